@@ -1,0 +1,42 @@
+// Host-side helpers shared by all translation units: error reporting across the C ABI and TMA
+// tensor-map construction (driver entry point resolved at run time, so the library links without libcuda).
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace pn {
+
+// Error codes returned over the C ABI (see include/panacea_b200.h).
+enum : int { PN_OK = 0, PN_ERR_INVALID = -1, PN_ERR_CUDA = -2, PN_ERR_UNSUPPORTED = -3 };
+
+void set_last_error(const std::string& msg);
+int fail(int code, const char* fmt, ...);
+
+#define PN_CHECK_CUDA(expr)                                                                       \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      return ::pn::fail(::pn::PN_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                        __FILE__, __LINE__);                                                      \
+  } while (0)
+
+#define PN_REQUIRE(cond, ...)                                    \
+  do {                                                           \
+    if (!(cond)) return ::pn::fail(::pn::PN_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+// Encode a tiled bf16 tensor map. dims/strides are innermost-first; strides in ELEMENTS for dims 1..rank-1
+// (dim 0 is contiguous). box is innermost-first. swizzle_bytes in {0,32,64,128}.
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                   const uint64_t* strides_elems, const uint32_t* box, int swizzle_bytes);
+
+int cached_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_elems, const uint32_t* box, int swizzle_bytes);
+
+int sm_count();
+
+}  // namespace pn

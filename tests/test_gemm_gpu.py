@@ -1,0 +1,106 @@
+"""GPU parity of the tcgen05 GEMM / implicit-conv kernel against torch fp32 math on the same bf16 inputs."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from panacea_b200.ops import NativeOps
+    return NativeOps()
+
+
+def _rand(shape, seed, scale=1.0, dtype=torch.bfloat16):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dtype).cuda()
+
+
+def _check(got, ref, tol=2e-3, name=""):
+    got = got.float()
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-6
+    assert torch.isfinite(got).all(), f"{name}: non-finite output"
+    assert err <= tol * scale, f"{name}: max err {err:.4e} vs scale {scale:.3e}"
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 160, 64), (256, 160, 128), (1000, 320, 320), (777, 128, 192),
+                                   (4096, 2560, 320), (130, 96, 64), (154, 640, 1024), (64, 8, 64), (16, 1280, 320)])
+def test_plain_gemm(ops, M, N, K):
+    a = _rand((M, K), 1)
+    w = _rand((N, K), 2, K ** -0.5)
+    out = ops.gemm(a, w)
+    torch.cuda.synchronize()
+    _check(out, a.float() @ w.float().t(), name=f"gemm {M}x{N}x{K}")
+
+
+def test_gemm_bias_residual_inplace(ops):
+    M, N, K = 3000, 320, 640
+    a = _rand((M, K), 3); w = _rand((N, K), 4, K ** -0.5)
+    bias = _rand((N,), 5, dtype=torch.float32)
+    res = _rand((M, N), 6, dtype=torch.float32)
+    ref = a.float() @ w.float().t() + bias + res
+    out = ops.gemm(a, w, bias=bias, residual=res, out=res)  # aliasing allowed
+    torch.cuda.synchronize()
+    _check(out, ref, name="bias+residual")
+
+
+def test_gemm_bf16_out_and_rowvec(ops):
+    M, N, K = 2048, 640, 320
+    a = _rand((M, K), 7); w = _rand((N, K), 8, K ** -0.5)
+    rv = _rand((4, N), 9, dtype=torch.float32)
+    out = ops.gemm(a, w, rowvec=rv, rows_per_group=256, n_groups=4, out_dtype=torch.bfloat16)
+    torch.cuda.synchronize()
+    grp = (torch.arange(M, device="cuda") // 256) % 4
+    ref = a.float() @ w.float().t() + rv[grp]
+    _check(out, ref, tol=1e-2, name="bf16 out + rowvec")
+
+
+def test_gemm_geglu(ops):
+    M, C = 1500, 320
+    a = _rand((M, C), 10)
+    w = _rand((8 * C, C), 11, C ** -0.5)       # reference layout: rows [0,4C) value, [4C,8C) gate
+    b = _rand((8 * C,), 12, dtype=torch.float32)
+    wi = torch.stack([w[:4 * C], w[4 * C:]], 1).reshape(8 * C, C).contiguous()
+    bi = torch.stack([b[:4 * C], b[4 * C:]], 1).reshape(8 * C).contiguous()
+    out = ops.gemm(a, wi, bias=bi, geglu=True, out_dtype=torch.bfloat16)
+    torch.cuda.synchronize()
+    y = a.float() @ w.float().t() + b
+    ref = y[:, :4 * C] * F.gelu(y[:, 4 * C:])
+    _check(out, ref, tol=1e-2, name="geglu")
+
+
+def test_gemm_strided_view(ops):
+    M, C = 900, 320
+    qkv = _rand((M, 3 * C), 13)
+    w = _rand((C, C), 14, C ** -0.5)
+    out = ops.gemm(qkv[:, C:2 * C], w)
+    torch.cuda.synchronize()
+    _check(out, qkv[:, C:2 * C].float() @ w.float().t(), name="strided A")
+
+
+@pytest.mark.parametrize("NB,H,W,C,N", [(2, 8, 24, 64, 160), (3, 4, 42, 128, 320), (2, 32, 336, 320, 320),
+                                        (4, 16, 168, 64, 64), (16, 4, 42, 64, 160)])
+def test_conv3x3(ops, NB, H, W, C, N):
+    x = _rand((NB, H, W, C), 15)
+    w = _rand((N, C, 3, 3), 16, (9 * C) ** -0.5)
+    wp = w.permute(0, 2, 3, 1).reshape(N, 9 * C).contiguous()
+    bias = _rand((N,), 17, dtype=torch.float32)
+    out = ops.gemm(x, wp, bias=bias, taps=(3, 3))
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1).permute(0, 2, 3, 1)
+    _check(out.reshape(NB, H, W, N), ref, name=f"conv3x3 {NB}x{H}x{W}x{C}->{N}")
+
+
+@pytest.mark.parametrize("b,T,P,C", [(2, 8, 300, 64), (1, 8, 2688, 320), (2, 4, 128, 128)])
+def test_temporal_conv(ops, b, T, P, C):
+    x = _rand((b, T, P, C), 18)
+    w = _rand((C, C, 3), 19, (3 * C) ** -0.5)          # Conv1d weight [Cout, Cin, k]
+    wp = w.permute(0, 2, 1).reshape(C, 3 * C).contiguous()
+    res = _rand((b, T, P, C), 20, dtype=torch.float32)
+    out = ops.gemm(x, wp, taps=(3, 1), residual=res)
+    torch.cuda.synchronize()
+    xin = x.float().permute(0, 2, 3, 1).reshape(b * P, C, T)
+    ref = F.conv1d(xin, w.float(), padding=1).reshape(b, P, C, T).permute(0, 3, 1, 2) + res
+    _check(out.reshape(b, T, P, C), ref, name="temporal conv")
