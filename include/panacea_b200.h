@@ -65,6 +65,96 @@ typedef struct pn_gemm_args {
 
 int pn_gemm(const pn_gemm_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * pn_attention — tcgen05 flash attention over view-tiled tokens (head_dim 64).
+ * Replaces: xformers.ops.memory_efficient_attention inside MemoryEfficientIntraViewAttention.forward
+ * (attention.py:407-489) and MemoryEfficientInterViewAttentionTwo.forward (attention.py:518-610), and
+ * F.scaled_dot_product_attention inside CrossAttention.forward for the 77-token text context
+ * (attention.py:229-291). Query tokens are a grid [F, H, V, W] (frame, row, view, column) with token
+ * stride q_ld; key/value tokens a grid [F / kv_frame_div, Hk, Vk, Wk] with stride kv_ld. Query view v
+ * attends the key views kv_views[v][0 .. kv_view_count[v]) (all rows/columns of those views):
+ *   intra-view : kv_views[v] = {v};   cross-view : the reference's table {5,1},{0,2},{1,3},{2,4},{3,5},{4};
+ *   text       : V = Vk = 1, W = tokens per batch element, Wk = 77, kv_views[0] = {0}.
+ * out[token, head*64 + d] = softmax(q k^T * scale) v, bf16, token stride out_ld.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pn_attn_args {
+  const void* q;   /* bf16, channel 0 of head 0 of the first query token */
+  const void* k;   /* bf16, likewise for keys (may point into the same fused qkv buffer) */
+  const void* v;
+  void* out;       /* bf16 */
+  int64_t q_ld, kv_ld, out_ld;
+  int64_t F, H, V, W;
+  int64_t Hk, Vk, Wk;
+  int32_t kv_frame_div;
+  int32_t heads, head_dim;
+  int32_t kv_views[8][2];
+  int32_t kv_view_count[8];
+  float scale;
+} pn_attn_args;
+
+int pn_attention(const pn_attn_args* args, void* stream);
+
+/* Temporal self-attention over T <= 16 frames per pixel (attention.py:1116-1125 -> :229-291, context=None).
+ * q/k/v/out bf16 [batch, T, pixels, ld]; one (batch, pixel, head) sequence per warp, fp32 softmax. */
+int pn_attention_temporal(const void* q, const void* k, const void* v, void* out, int64_t batch, int64_t T,
+                          int64_t pixels, int32_t heads, int32_t head_dim, int64_t ld, int64_t out_ld, float scale,
+                          void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Normalisation (fp32 residual stream in, bf16 MMA operand out)
+ * ---------------------------------------------------------------------------------------------- */
+/* GroupNorm(32, C) over (C/32, all pixels of a frame) [+ SiLU]: util.py:276-283 (eps 1e-5, ResBlock3D
+ * in/out_layers, openaimodel.py:413,455) and attention.py:129-132 (eps 1e-6, STT norm*). The statistics span
+ * all six views of the panorama. raw_bf16 (optional) receives a plain bf16 cast of x (input of the 1x1 skip
+ * convolution, openaimodel.py:486). workspace: pn_groupnorm_workspace_floats(...) floats. */
+int64_t pn_groupnorm_workspace_floats(int64_t frames, int64_t pixels, int64_t channels);
+int pn_groupnorm_silu(const float* x, const float* gamma, const float* beta, void* y_bf16, void* raw_bf16,
+                      float* workspace, int64_t frames, int64_t pixels, int64_t channels, float eps, int act_silu,
+                      void* stream);
+/* GroupNorm(32, C) over (C/32, T) per pixel [+ SiLU] on x[batch, T, pixels, C]: the reference applies
+ * nn.GroupNorm to the "(b h w) c t" rearrangement (openaimodel.py:509-512, 534-537). */
+int pn_groupnorm_pixel_silu(const float* x, const float* gamma, const float* beta, void* y_bf16, int64_t batch,
+                            int64_t frames_per_seq, int64_t pixels, int64_t channels, float eps, int act_silu,
+                            void* stream);
+/* nn.LayerNorm(C) per token, eps 1e-5 (attention.py:699-701). */
+int pn_layernorm(const float* x, const float* gamma, const float* beta, void* y_bf16, int64_t rows, int64_t channels,
+                 float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Convolutions that cannot feed a 64-wide UMMA K block, layout and sampler helpers
+ * ---------------------------------------------------------------------------------------------- */
+/* Direct 3x3 conv, pad 1, stride 1|2, channels-last (stem openaimodel.py:977, head :1251, BEV hint stem
+ * controlmodel.py:43-59). w_packed fp32 [9][Cin][Cout_pad]; y = act(conv + bias) + addend. */
+int pn_conv3x3_direct(const void* x, int x_is_bf16, const float* w_packed, const float* bias, const float* addend,
+                      float* y_f32, void* y_bf16, int64_t frames, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
+                      int64_t Cout_pad, int stride, int act_silu, void* stream);
+/* im2col for the stride-2 Downsample conv (openaimodel.py:187): fp32 [F,H,W,C] -> bf16 [F*Ho*Wo, 9*C]. */
+int pn_im2col3x3_s2(const float* x, void* out_bf16, int64_t frames, int64_t H, int64_t W, int64_t C, void* stream);
+/* F.interpolate(scale_factor=2, mode="nearest") of Upsample (openaimodel.py:133-140), fp32 -> bf16. */
+int pn_upsample2x_bf16(const float* x, void* y_bf16, int64_t frames, int64_t H, int64_t W, int64_t C, void* stream);
+/* out = cat([h, skip + ctrl], channel) — decoder skip join (controlmodel.py:193-195); ctrl may be NULL. */
+int pn_concat_add(const float* h, const float* skip, const float* ctrl, float* out, int64_t rows, int64_t C1,
+                  int64_t C2, void* stream);
+int pn_add_inplace(float* x, const float* y, int64_t n, void* stream);      /* h += control.pop() (controlmodel.py:192) */
+int pn_cast_bf16(const float* x, void* y_bf16, int64_t n, void* stream);
+/* [batch, A, B] -> out[batch, B, ld] at column offset off: NCHW <-> channels-last at the module boundary
+ * (also performs the channel concat of wrappers.py:41). */
+int pn_transpose_f32(const float* in, float* out, int64_t batch, int64_t A, int64_t B, int64_t out_ld, int64_t out_off,
+                     void* stream);
+/* util.py:224-248 timestep_embedding (cos | sin halves). */
+int pn_timestep_embedding(const int64_t* t, float* out, int64_t n, int64_t dim, void* stream);
+/* y = act_out(W act_in(x) + b) for M <= 32 rows: time_embed MLP and per-block emb_layers
+ * (openaimodel.py:936-943, 439-445). */
+int pn_linear_small(const float* x, const void* W_bf16, const float* bias, float* y, int64_t M, int64_t N, int64_t K,
+                    int64_t ldy, int silu_in, int silu_out, void* stream);
+/* One Euler step with classifier-free guidance, reference operation order (denoiser.py:22-28, guiders.py:25-29,
+ * sampling_utils.py:7-9,39-40, sampling.py:103-110). eps2 = [uncond ; cond] halves of n elements each;
+ * x is updated in place; x_in_next (optional, 2n elements) receives x_new * c_in_next duplicated. */
+int pn_cfg_euler_step(float* x, const float* eps2, float* x_in_next, int64_t n, float sigma, float sigma_next,
+                      float cfg_scale, float c_in_next, void* stream);
+/* out[c*n + i] = x[i] * s for c < copies (prepare_sampling_loop x *= sqrt(1+sigma0^2), CFG batch doubling). */
+int pn_scale_dup(const float* x, float* out, int64_t n, float s, int copies, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,124 @@
+"""TEST INFRASTRUCTURE — generates tests/golden/*.pt by running the UNMODIFIED reference modules
+(/root/reference, imported through oracle/ref_loader.py) on the seeded cases of oracle/cases.py.
+
+Run in the build container only:  python -m oracle.make_golden [--only name,...] [--skip-full]
+Outputs are small (the reference OUTPUT tensors + known-answer values); inputs/weights are re-derived
+from seeds by whoever consumes a fixture.
+"""
+from __future__ import annotations
+
+import argparse
+import sys
+import time
+from pathlib import Path
+
+import torch
+
+from . import cases as Cs
+from . import ref_loader as R
+from . import unet_port as P
+
+GOLDEN = Path(__file__).resolve().parent.parent / "tests" / "golden"
+
+
+@torch.no_grad()
+def golden_eps(case: Cs.EpsCase) -> dict:
+    kw = case.unet_kwargs()
+    model = R.build_reference_model(kw)
+    sd = Cs.make_weights(case)
+    missing = model.load_state_dict(sd, strict=True)
+    x, t, c = Cs.make_inputs(case)
+    t0 = time.time()
+    with R.view_height_shim(case.H, case.w):
+        eps = model(x, t, dict(c))
+    dt = time.time() - t0
+    return {"meta": case.meta(), "eps": eps.contiguous(), "seconds": dt, "torch": torch.__version__,
+            "threads": torch.get_num_threads()}
+
+
+@torch.no_grad()
+def golden_kat() -> dict:
+    """Known-answer values of the sampler stack and embeddings, from the reference classes."""
+    ref = R.import_reference()
+    disc = ref.discretizer.LegacyDDPMDiscretization()
+    out = {"sigmas_25": disc(25), "sigmas_50": disc(50), "sigmas_10": disc(10)}
+    den = ref.denoiser.DiscreteDenoiser(
+        weighting_config={"target": "sgm.modules.diffusionmodules.denoiser_weighting.EpsWeighting"},
+        scaling_config={"target": "sgm.modules.diffusionmodules.denoiser_scaling.EpsScaling"},
+        num_idx=1000,
+        discretization_config={"target": "sgm.modules.diffusionmodules.discretizer.LegacyDDPMDiscretization"})
+    out["denoiser_sigmas"] = den.sigmas.clone()
+    out["idx_of_sigmas_25"] = den.sigma_to_idx(out["sigmas_25"][:-1])
+    out["idx_of_sigmas_50"] = den.sigma_to_idx(out["sigmas_50"][:-1])
+    out["pos_embed_T4_C8"] = ref.attention.create_1d_absolute_sin_cos_embedding(4, 8)
+    out["pos_embed_T8_C64"] = ref.attention.create_1d_absolute_sin_cos_embedding(8, 64)
+    out["timestep_embedding_320"] = ref.util.timestep_embedding(torch.tensor([0, 39, 500, 999]), 320)
+    return out
+
+
+@torch.no_grad()
+def golden_sampler(case: Cs.EpsCase, num_steps: int = 10, scale: float = 5.0) -> dict:
+    """Full reference loop: EulerEDMSampler + VanillaCFG + DiscreteDenoiser around the reference wrapper."""
+    ref = R.import_reference()
+    model = R.build_reference_model(case.unet_kwargs())
+    model.load_state_dict(Cs.make_weights(case), strict=True)
+    den = ref.denoiser.DiscreteDenoiser(
+        weighting_config={"target": "sgm.modules.diffusionmodules.denoiser_weighting.EpsWeighting"},
+        scaling_config={"target": "sgm.modules.diffusionmodules.denoiser_scaling.EpsScaling"},
+        num_idx=1000,
+        discretization_config={"target": "sgm.modules.diffusionmodules.discretizer.LegacyDDPMDiscretization"})
+    sampler = ref.sampling.EulerEDMSampler(
+        num_steps=num_steps, device="cpu",
+        discretization_config={"target": "sgm.modules.diffusionmodules.discretizer.LegacyDDPMDiscretization"},
+        guider_config={"target": "sgm.modules.diffusionmodules.guiders.VanillaCFG", "params": {"scale": scale}})
+    x, c, uc = sampler_inputs(case)
+    calls = []
+
+    def denoise(xx, sigma, cc):
+        calls.append(int(den.sigma_to_idx(sigma)[0]))
+        return den(model, xx, sigma, cc)
+
+    with R.view_height_shim(case.H, case.w):
+        out = sampler(denoise, x.clone(), c, uc)
+    return {"meta": case.meta(), "num_steps": num_steps, "scale": scale, "x_final": out, "timestep_indices": calls}
+
+
+def sampler_inputs(case: Cs.EpsCase):
+    """One sequence (case.b is ignored: the sampler doubles the batch itself): init noise, c and uc dicts."""
+    g = torch.Generator(device="cpu").manual_seed(case.input_seed + 100)
+    T, W = case.num_frames, 6 * case.w
+    x = torch.randn(T, 4, case.H, W, generator=g)
+    concat = torch.randn(T, 4, case.H, W, generator=g)
+    hint = torch.rand(T, 19, 8 * case.H, 8 * W, generator=g)
+    c = {"concat": concat, "cond_feat": hint, "crossattn": torch.randn(1, 77, case.context_dim, generator=g)}
+    uc = {"concat": concat, "cond_feat": hint, "crossattn": torch.randn(1, 77, case.context_dim, generator=g)}
+    return x, c, uc
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    ap.add_argument("--skip-full", action="store_true")
+    a = ap.parse_args(argv)
+    only = set(filter(None, a.only.split(",")))
+    GOLDEN.mkdir(parents=True, exist_ok=True)
+    if not only or "kat" in only:
+        torch.save(golden_kat(), GOLDEN / "kat.pt")
+        print("kat.pt")
+    for case in Cs.GOLDEN_CASES:
+        if only and case.name not in only:
+            continue
+        if a.skip_full and case.model_channels >= 320:
+            continue
+        g = golden_eps(case)
+        torch.save(g, GOLDEN / f"eps_{case.name}.pt")
+        print(f"eps_{case.name}.pt  {tuple(g['eps'].shape)}  rms={g['eps'].pow(2).mean().sqrt():.4f}  {g['seconds']:.1f}s")
+    if not only or "sampler" in only:
+        case = Cs.GOLDEN_CASES[0]
+        g = golden_sampler(case)
+        torch.save(g, GOLDEN / f"sampler_{case.name}.pt")
+        print(f"sampler_{case.name}.pt rms={g['x_final'].pow(2).mean().sqrt():.4f} idx={g['timestep_indices']}")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])

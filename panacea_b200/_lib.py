@@ -31,12 +31,44 @@ class GemmArgs(C.Structure):
     ]
 
 
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("out", C.c_void_p),
+        ("q_ld", C.c_int64), ("kv_ld", C.c_int64), ("out_ld", C.c_int64),
+        ("F", C.c_int64), ("H", C.c_int64), ("V", C.c_int64), ("W", C.c_int64),
+        ("Hk", C.c_int64), ("Vk", C.c_int64), ("Wk", C.c_int64),
+        ("kv_frame_div", C.c_int32), ("heads", C.c_int32), ("head_dim", C.c_int32),
+        ("kv_views", (C.c_int32 * 2) * 8), ("kv_view_count", C.c_int32 * 8),
+        ("scale", C.c_float),
+    ]
+
+
+_vp, _i64, _i32, _f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float
+
 # name -> (restype, argtypes); every symbol declared in include/panacea_b200.h must appear here
 # (tests/test_abi.py checks the header against this table and against the built library).
 SIGNATURES: dict[str, tuple] = {
     "pn_last_error": (C.c_char_p, []),
     "pn_abi_version": (C.c_int, []),
     "pn_gemm": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
+    "pn_attention": (C.c_int, [C.POINTER(AttnArgs), _vp]),
+    "pn_attention_temporal": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _i64, _i64, _f32, _vp]),
+    "pn_groupnorm_workspace_floats": (_i64, [_i64, _i64, _i64]),
+    "pn_groupnorm_silu": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _f32, C.c_int, _vp]),
+    "pn_groupnorm_pixel_silu": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _f32, C.c_int, _vp]),
+    "pn_layernorm": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _f32, _vp]),
+    "pn_conv3x3_direct": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64,
+                                    C.c_int, C.c_int, _vp]),
+    "pn_im2col3x3_s2": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp]),
+    "pn_upsample2x_bf16": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp]),
+    "pn_concat_add": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
+    "pn_add_inplace": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "pn_cast_bf16": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "pn_transpose_f32": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp]),
+    "pn_timestep_embedding": (C.c_int, [_vp, _vp, _i64, _i64, _vp]),
+    "pn_linear_small": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, C.c_int, C.c_int, _vp]),
+    "pn_cfg_euler_step": (C.c_int, [_vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _vp]),
+    "pn_scale_dup": (C.c_int, [_vp, _vp, _i64, _f32, C.c_int, _vp]),
 }
 
 

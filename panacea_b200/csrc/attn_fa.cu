@@ -1,0 +1,363 @@
+// tcgen05 flash attention for the decomposed-4D attention of Panacea (head_dim 64, bf16 operands, fp32 softmax).
+//
+// One kernel serves the three tensor-core attention variants; they differ only in which K/V tiles a query tile
+// visits, and every tile is a TMA box of ONE rank-5 tensor map over the token buffer [F, H, V, w, C]
+// (frames, latent rows, views, columns per view, channels) — the views are never sliced or copied:
+//   * intra-view  (attention.py:407-489)  : K/V = the query's own view;
+//   * cross-view  (attention.py:518-610)  : K/V = the neighbour views from a table
+//                                            {5,1},{0,2},{1,3},{2,4},{3,5},{4} (the reference's asymmetric ring);
+//   * text cross-attention (attention.py:229-291, 77 keys): V=1, one K/V block per batch element, tail masked.
+// (Temporal self-attention over T<=16 frames is a CUDA-core kernel, attn_small.cu.)
+//
+// CTA = one query tile (<=128 queries of one frame/view/head). Warp roles:
+//   warp 0: TMA producer (Q once; K and V boxes through a 3-stage ring)
+//   warp 1: UMMA issuer   S = Q K^T  (M=128, N=kv_n, K=64)  -> TMEM, double buffered
+//                         PV = P V   (M=128, N=64,  K=kv_n) -> TMEM, double buffered (V is the MN-major B operand)
+//   warps 2-5: softmax, one thread per query row (TMEM lane == row, so max/sum need no shuffles):
+//              tcgen05.ld S -> running max -> exp2 -> bf16 P into 128B-swizzled smem (A operand of PV);
+//              O accumulates in registers with the usual rescale; the PV of block j-1 is folded in while the
+//              tensor core works on block j.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "../../include/panacea_b200.h"
+
+namespace pn {
+
+constexpr int FA_D = 64;
+constexpr int FA_STAGES = 3;
+constexpr int FA_THREADS = 192;
+constexpr int FA_TILE_BYTES = 128 * 128;          // 128 rows x 64 bf16
+constexpr int FA_SMEM_Q = 0;
+constexpr int FA_SMEM_K = FA_TILE_BYTES;
+constexpr int FA_SMEM_V = FA_SMEM_K + FA_STAGES * FA_TILE_BYTES;
+constexpr int FA_SMEM_P = FA_SMEM_V + FA_STAGES * FA_TILE_BYTES;   // 2 buffers x 2 atoms x 16 KB
+constexpr int FA_SMEM_BAR = FA_SMEM_P + 4 * FA_TILE_BYTES;
+constexpr int FA_SMEM_TOTAL = FA_SMEM_BAR + 256 + 1024;
+
+struct FaParams {
+  CUtensorMap mapQ;
+  CUtensorMap mapK;
+  CUtensorMap mapV;
+  int q_ch0, k_ch0, v_ch0;     // channel offset of head 0 inside a token row
+  int heads;
+  int F, H, V, W;              // query token grid
+  int qw, qh, tiles_x, tiles_y;
+  int kw, kh, kv_rows, kv_n, kv_yblocks;
+  int kv_views[8][2];
+  int kv_view_count[8];
+  int kv_frame_div;            // kv frame = q frame / kv_frame_div
+  float scale_log2;            // softmax scale * log2(e)
+  __nv_bfloat16* out;
+  long long out_ld;            // token stride of out (elements)
+  int out_ch0;
+};
+
+__global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_constant__ FaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FA_SMEM_BAR);
+  uint64_t* q_full = bars;                     // [1]
+  uint64_t* k_full = bars + 1;                 // [3]
+  uint64_t* v_full = bars + 4;                 // [3]
+  uint64_t* kv_empty = bars + 7;               // [3]
+  uint64_t* s_full = bars + 10;                // [2]
+  uint64_t* s_empty = bars + 12;               // [2]
+  uint64_t* p_full = bars + 14;                // [2]
+  uint64_t* pv_full = bars + 16;               // [2]
+  uint64_t* pv_empty = bars + 18;              // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tile decode: q tile fastest so that concurrently resident CTAs share K/V in L2
+  int bid = blockIdx.x;
+  const int tx = bid % p.tiles_x; bid /= p.tiles_x;
+  const int ty = bid % p.tiles_y; bid /= p.tiles_y;
+  const int head = bid % p.heads; bid /= p.heads;
+  const int view = bid % p.V; bid /= p.V;
+  const int frame = bid;
+  const int x0 = tx * p.qw, y0 = ty * p.qh;
+  const int nviews = p.kv_view_count[view];
+  const int nblk = nviews * p.kv_yblocks;
+  const int kv_frame = frame / p.kv_frame_div;
+
+  // zero K/V/Q staging once: rows a TMA box does not cover (kv_rows..kv_n) must read as 0, never as stale NaNs
+  {
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    for (int i = threadIdx.x; i < FA_SMEM_P / 16; i += FA_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.mapQ);
+    tma_prefetch_desc(&p.mapK);
+    tma_prefetch_desc(&p.mapV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < FA_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 128);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&pv_full[i], 1);
+      mbar_init(&pv_empty[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tm_S = tmem_base;          // 2 x 128 columns
+  const uint32_t tm_PV = tmem_base + 256;   // 2 x 64 columns
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const uint32_t q_bytes = (uint32_t)(p.qw * p.qh) * 128u;
+      const uint32_t kv_bytes = (uint32_t)p.kv_rows * 128u;
+      mbar_arrive_expect_tx(q_full, q_bytes);
+      tma_load_5d(smem + FA_SMEM_Q, &p.mapQ, q_full, p.q_ch0 + head * FA_D, x0, view, y0, frame);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < nblk; ++i) {
+        const int vi = i / p.kv_yblocks, yb = i - vi * p.kv_yblocks;
+        const int kvv = p.kv_views[view][vi];
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&k_full[stage], kv_bytes);
+        tma_load_5d(smem + FA_SMEM_K + stage * FA_TILE_BYTES, &p.mapK, &k_full[stage], p.k_ch0 + head * FA_D, 0, kvv,
+                    yb * p.kh, kv_frame);
+        mbar_arrive_expect_tx(&v_full[stage], kv_bytes);
+        tma_load_5d(smem + FA_SMEM_V + stage * FA_TILE_BYTES, &p.mapV, &v_full[stage], p.v_ch0 + head * FA_D, 0, kvv,
+                    yb * p.kh, kv_frame);
+        if (++stage == FA_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== UMMA issuer =====================
+    const uint32_t idesc_s = umma_idesc_bf16(128, p.kv_n, 0, 0);      // S = Q K^T : both K-major
+    const uint32_t idesc_pv = umma_idesc_bf16(128, FA_D, 0, 1);       // PV: A = P K-major, B = V MN-major
+    const uint32_t sQ = smem_u32(smem + FA_SMEM_Q);
+    const int ksteps_pv = p.kv_n / 16;
+    mbar_wait(q_full, 0);
+    auto issue_pv = [&](int i) {
+      const int st = i % FA_STAGES, buf = i & 1;
+      mbar_wait(&v_full[st], (uint32_t)((i / FA_STAGES) & 1));
+      mbar_wait(&p_full[buf], (uint32_t)((i >> 1) & 1));
+      mbar_wait(&pv_empty[buf], (uint32_t)(((i >> 1) & 1) ^ 1));
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sP = smem_u32(smem + FA_SMEM_P + buf * 2 * FA_TILE_BYTES);
+        const uint32_t sV = smem_u32(smem + FA_SMEM_V + st * FA_TILE_BYTES);
+        for (int k = 0; k < ksteps_pv; ++k) {
+          const uint64_t da = umma_smem_desc(sP + (k >> 2) * FA_TILE_BYTES + (k & 3) * 32, 16, 1024);
+          const uint64_t db = umma_smem_desc(sV + k * 2048, 1024, 1024);   // 16 keys (rows of 128 B) per K step
+          umma_f16_ss(tm_PV + buf * FA_D, da, db, idesc_pv, k > 0 ? 1u : 0u);
+        }
+        umma_commit(&pv_full[buf]);
+        umma_commit(&kv_empty[st]);
+      }
+      __syncwarp();
+    };
+    for (int j = 0; j < nblk; ++j) {
+      const int st = j % FA_STAGES, buf = j & 1;
+      mbar_wait(&k_full[st], (uint32_t)((j / FA_STAGES) & 1));
+      mbar_wait(&s_empty[buf], (uint32_t)(((j >> 1) & 1) ^ 1));
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sK = smem_u32(smem + FA_SMEM_K + st * FA_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < FA_D / 16; ++k) {
+          const uint64_t da = umma_smem_desc(sQ + k * 32, 16, 1024);
+          const uint64_t db = umma_smem_desc(sK + k * 32, 16, 1024);
+          umma_f16_ss(tm_S + buf * 128, da, db, idesc_s, k > 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[buf]);
+      }
+      __syncwarp();
+      if (j > 0) issue_pv(j - 1);
+    }
+    issue_pv(nblk - 1);
+  } else {
+    // ===================== softmax / output warps: thread == query row =====================
+    const int lane_grp = warp & 3;
+    const int row = lane_grp * 32 + lane;
+    const uint32_t lane_addr = uint32_t(lane_grp * 32) << 16;
+    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
+    float O[FA_D];
+#pragma unroll
+    for (int i = 0; i < FA_D; ++i) O[i] = 0.f;
+    const int nchunk = p.kv_n / 16;
+    const float c = p.scale_log2;
+
+    auto consume_pv = [&](int i, float alpha) {
+      const int buf = i & 1;
+      mbar_wait(&pv_full[buf], (uint32_t)((i >> 1) & 1));
+      tc_fence_after();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t v[32];
+        tmem_ld_32x32(tm_PV + lane_addr + buf * FA_D + h * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int t = 0; t < 32; ++t) O[h * 32 + t] = O[h * 32 + t] * alpha + __uint_as_float(v[t]);
+      }
+      tc_fence_before();
+      mbar_arrive(&pv_empty[buf]);
+    };
+
+    for (int j = 0; j < nblk; ++j) {
+      const int buf = j & 1;
+      mbar_wait(&s_full[buf], (uint32_t)((j >> 1) & 1));
+      tc_fence_after();
+      const uint32_t tS = tm_S + lane_addr + buf * 128;
+      // pass 1: row maximum (columns >= kv_rows are padding)
+      float mx = -INFINITY;
+      for (int ch = 0; ch < nchunk; ++ch) {
+        uint32_t v[16];
+        tmem_ld_32x16(tS + ch * 16, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int t = 0; t < 16; ++t)
+          if (ch * 16 + t < p.kv_rows) mx = fmaxf(mx, __uint_as_float(v[t]));
+      }
+      const float m_new = fmaxf(m_run, mx * c);
+      const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_new);
+      // pass 2: p = exp2(s*c - m_new), row sum, bf16 P into the swizzled A-operand buffer
+      float rs = 0.f;
+      uint8_t* sP = smem + FA_SMEM_P + buf * 2 * FA_TILE_BYTES;
+      for (int ch = 0; ch < nchunk; ++ch) {
+        uint32_t v[16];
+        tmem_ld_32x16(tS + ch * 16, v);
+        tmem_ld_wait();
+        float e[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+          const float pv = exp2f(__uint_as_float(v[t]) * c - m_new);
+          e[t] = (ch * 16 + t < p.kv_rows) ? pv : 0.f;
+          rs += e[t];
+        }
+        // 16 keys = 2 chunks of 16 B inside atom (ch/4); chunk index within the 128 B row = (ch%4)*2 + {0,1}
+        uint8_t* atom = sP + (ch >> 2) * FA_TILE_BYTES + row * 128;
+        const int c0 = (ch & 3) * 2;
+        *reinterpret_cast<uint4*>(atom + ((c0 ^ (row & 7)) << 4)) =
+            make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
+        *reinterpret_cast<uint4*>(atom + (((c0 + 1) ^ (row & 7)) << 4)) =
+            make_uint4(pack_bf16x2(e[8], e[9]), pack_bf16x2(e[10], e[11]), pack_bf16x2(e[12], e[13]), pack_bf16x2(e[14], e[15]));
+      }
+      tc_fence_before();
+      mbar_arrive(&s_empty[buf]);
+      fence_proxy_async_smem();
+      mbar_arrive(&p_full[buf]);
+      l_run = l_run * alpha + rs;
+      m_run = m_new;
+      if (j > 0) consume_pv(j - 1, alpha_prev);
+      alpha_prev = alpha;
+    }
+    consume_pv(nblk - 1, alpha_prev);
+
+    // normalise and store this row
+    const int yy = row / p.qw, xx = row - yy * p.qw;
+    const int x = x0 + xx, y = y0 + yy;
+    if (row < p.qw * p.qh && x < p.W && y < p.H) {
+      const float inv = 1.f / l_run;
+      const long long token = (((long long)frame * p.H + y) * p.V + view) * p.W + x;
+      __nv_bfloat16* dst = p.out + token * p.out_ld + p.out_ch0 + head * FA_D;
+#pragma unroll
+      for (int i = 0; i < FA_D / 8; ++i) {
+        *reinterpret_cast<uint4*>(dst + i * 8) =
+            make_uint4(pack_bf16x2(O[i * 8 + 0] * inv, O[i * 8 + 1] * inv), pack_bf16x2(O[i * 8 + 2] * inv, O[i * 8 + 3] * inv),
+                       pack_bf16x2(O[i * 8 + 4] * inv, O[i * 8 + 5] * inv), pack_bf16x2(O[i * 8 + 6] * inv, O[i * 8 + 7] * inv));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace pn
+
+using namespace pn;
+
+extern "C" int pn_attention(const pn_attn_args* a, void* stream_v) {
+  if (a == nullptr) return fail(PN_ERR_INVALID, "pn_attention: null args");
+  PN_REQUIRE(a->q && a->k && a->v && a->out, "pn_attention: null tensor pointer");
+  PN_REQUIRE(a->head_dim == FA_D, "pn_attention: head_dim %d unsupported (64 only)", a->head_dim);
+  PN_REQUIRE(a->heads > 0 && a->F > 0 && a->H > 0 && a->V > 0 && a->V <= 8 && a->W > 0, "pn_attention: bad query geometry");
+  PN_REQUIRE(a->Hk > 0 && a->Vk > 0 && a->Vk <= 8 && a->Wk > 0 && a->kv_frame_div > 0, "pn_attention: bad key geometry");
+  PN_REQUIRE(a->q_ld % 8 == 0 && a->kv_ld % 8 == 0 && a->out_ld % 8 == 0, "pn_attention: token strides must be multiples of 8");
+  PN_REQUIRE(a->q_ld >= a->heads * FA_D && a->kv_ld >= a->heads * FA_D && a->out_ld >= a->heads * FA_D,
+             "pn_attention: token stride smaller than heads*64");
+
+  FaParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.heads = a->heads;
+  p.F = (int)a->F; p.H = (int)a->H; p.V = (int)a->V; p.W = (int)a->W;
+  // query tile: full view width when it fits, as many rows as keep <= 128 queries
+  p.qw = (int)(a->W <= 128 ? a->W : 128);
+  p.qh = 128 / p.qw;
+  if (p.qh > a->H) p.qh = (int)a->H;
+  if (p.qh < 1) p.qh = 1;
+  p.tiles_x = (int)((a->W + p.qw - 1) / p.qw);
+  p.tiles_y = (int)((a->H + p.qh - 1) / p.qh);
+  // key block: full key-view width (must fit one block row-wise), rows = largest divisor of Hk with <= 128 keys
+  PN_REQUIRE(a->Wk <= 128, "pn_attention: key view width %lld > 128 unsupported", (long long)a->Wk);
+  p.kw = (int)a->Wk;
+  int kh = 128 / p.kw;
+  if (kh > a->Hk) kh = (int)a->Hk;
+  while (kh > 1 && (a->Hk % kh) != 0) --kh;
+  p.kh = kh;
+  p.kv_rows = p.kw * p.kh;
+  p.kv_n = (p.kv_rows + 15) / 16 * 16;
+  p.kv_yblocks = (int)(a->Hk / p.kh);
+  for (int v = 0; v < a->V; ++v) {
+    const int cnt = a->kv_view_count[v];
+    PN_REQUIRE(cnt >= 1 && cnt <= 2, "pn_attention: kv_view_count[%d]=%d must be 1 or 2", v, cnt);
+    p.kv_view_count[v] = cnt;
+    for (int i = 0; i < cnt; ++i) {
+      PN_REQUIRE(a->kv_views[v][i] >= 0 && a->kv_views[v][i] < a->Vk, "pn_attention: kv view out of range");
+      p.kv_views[v][i] = a->kv_views[v][i];
+    }
+  }
+  p.kv_frame_div = a->kv_frame_div;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
+  p.out_ld = a->out_ld;
+  p.q_ch0 = 0; p.k_ch0 = 0; p.v_ch0 = 0; p.out_ch0 = 0;
+
+  const uint64_t chq = (uint64_t)a->heads * FA_D;
+  {
+    const uint64_t dims[5] = {chq, (uint64_t)a->W, (uint64_t)a->V, (uint64_t)a->H, (uint64_t)a->F};
+    const uint64_t ld = (uint64_t)a->q_ld;
+    const uint64_t str[4] = {ld, ld * a->W, ld * a->W * a->V, ld * a->W * a->V * a->H};
+    const uint32_t box[5] = {64u, (uint32_t)p.qw, 1u, (uint32_t)p.qh, 1u};
+    int rc = cached_tmap_bf16(&p.mapQ, a->q, 5, dims, str, box, 128);
+    if (rc != PN_OK) return rc;
+  }
+  {
+    const uint64_t Fk = (uint64_t)((a->F + a->kv_frame_div - 1) / a->kv_frame_div);
+    const uint64_t dims[5] = {chq, (uint64_t)a->Wk, (uint64_t)a->Vk, (uint64_t)a->Hk, Fk};
+    const uint64_t ld = (uint64_t)a->kv_ld;
+    const uint64_t str[4] = {ld, ld * a->Wk, ld * a->Wk * a->Vk, ld * a->Wk * a->Vk * a->Hk};
+    const uint32_t box[5] = {64u, (uint32_t)p.kw, 1u, (uint32_t)p.kh, 1u};
+    int rc = cached_tmap_bf16(&p.mapK, a->k, 5, dims, str, box, 128);
+    if (rc != PN_OK) return rc;
+    rc = cached_tmap_bf16(&p.mapV, a->v, 5, dims, str, box, 128);
+    if (rc != PN_OK) return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    PN_CHECK_CUDA(cudaFuncSetAttribute(attn_fa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_TOTAL));
+    attr_set = true;
+  }
+  const long long grid = (long long)p.tiles_x * p.tiles_y * a->heads * a->V * a->F;
+  PN_REQUIRE(grid > 0 && grid < (1ll << 31), "pn_attention: grid too large");
+  attn_fa_kernel<<<(unsigned)grid, FA_THREADS, FA_SMEM_TOTAL, reinterpret_cast<cudaStream_t>(stream_v)>>>(p);
+  PN_CHECK_CUDA(cudaGetLastError());
+  return PN_OK;
+}

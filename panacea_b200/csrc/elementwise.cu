@@ -1,0 +1,313 @@
+// Small HBM-bound helpers of the denoising path: layout changes at the NCHW module boundary, nearest 2x
+// upsampling, skip concatenation, timestep embedding, the tiny time-embedding linears, stride-2 im2col and the
+// fused classifier-free-guidance + Euler update of the sampler.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "../../include/panacea_b200.h"
+
+namespace pn {
+
+// ---------------------------------------------------------------- [F, A, B] -> out[f, b, off + a] (row stride ld)
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int A, int B, long long ld,
+                                 int off) {
+  __shared__ float tile[32][33];
+  const int f = blockIdx.z;
+  const int b0 = blockIdx.x * 32, a0 = blockIdx.y * 32;
+  const float* src = in + (size_t)f * A * B;
+  float* dst = out + (size_t)f * B * ld;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int a = a0 + i, b = b0 + threadIdx.x;
+    if (a < A && b < B) tile[i][threadIdx.x] = src[(size_t)a * B + b];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int b = b0 + i, a = a0 + threadIdx.x;
+    if (a < A && b < B) dst[(size_t)b * ld + off + a] = tile[threadIdx.x][i];
+  }
+}
+
+// ---------------------------------------------------------------- nearest 2x upsample, fp32 -> bf16
+__global__ void upsample2x_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int F, int H, int W,
+                                  int C) {
+  const int c8n = C / 8;
+  const size_t total = (size_t)F * (2 * H) * (2 * W) * c8n;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(e % c8n);
+    size_t r = e / c8n;
+    const int ox = (int)(r % (2 * W)); r /= (2 * W);
+    const int oy = (int)(r % (2 * H));
+    const int f = (int)(r / (2 * H));
+    const float* src = x + (((size_t)f * H + (oy >> 1)) * W + (ox >> 1)) * C + c8 * 8;
+    const float4 a = *reinterpret_cast<const float4*>(src);
+    const float4 b = *reinterpret_cast<const float4*>(src + 4);
+    *reinterpret_cast<uint4*>(y + (((size_t)f * 2 * H + oy) * 2 * W + ox) * C + c8 * 8) =
+        make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+  }
+}
+
+// ---------------------------------------------------------------- out = cat(h, skip (+ ctrl)) along channels
+__global__ void concat_add_kernel(const float* __restrict__ h, const float* __restrict__ skip,
+                                  const float* __restrict__ ctrl, float* __restrict__ out, long long rows, int C1,
+                                  int C2) {
+  const int Ct = C1 + C2;
+  const int c4n = Ct / 4;
+  const size_t total = (size_t)rows * c4n;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % c4n) * 4;
+    const size_t r = e / c4n;
+    float4 v;
+    if (c < C1) {
+      v = *reinterpret_cast<const float4*>(h + r * C1 + c);
+    } else {
+      v = *reinterpret_cast<const float4*>(skip + r * C2 + (c - C1));
+      if (ctrl) {
+        const float4 k = *reinterpret_cast<const float4*>(ctrl + r * C2 + (c - C1));
+        v.x += k.x; v.y += k.y; v.z += k.z; v.w += k.w;
+      }
+    }
+    *reinterpret_cast<float4*>(out + r * Ct + c) = v;
+  }
+}
+
+__global__ void add_inplace_kernel(float* __restrict__ x, const float* __restrict__ y, size_t n4) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (size_t)gridDim.x * blockDim.x) {
+    float4 a = reinterpret_cast<float4*>(x)[e];
+    const float4 b = reinterpret_cast<const float4*>(y)[e];
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    reinterpret_cast<float4*>(x)[e] = a;
+  }
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t n4) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (size_t)gridDim.x * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(x)[e];
+    reinterpret_cast<uint2*>(y)[e] = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+  }
+}
+
+// ---------------------------------------------------------------- sinusoidal timestep embedding
+// util.py:224-248: emb[n] = [cos(t f_k), sin(t f_k)], f_k = exp(-ln(10000) k / half)
+__global__ void timestep_embedding_kernel(const long long* __restrict__ t, float* __restrict__ out, int n, int dim) {
+  const int half = dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * half) return;
+  const int row = i / half, k = i - row * half;
+  const float freq = expf(-9.210340371976184f * (float)k / (float)half);
+  const float arg = (float)t[row] * freq;
+  out[(size_t)row * dim + k] = cosf(arg);
+  out[(size_t)row * dim + half + k] = sinf(arg);
+  if ((dim & 1) && k == 0) out[(size_t)row * dim + dim - 1] = 0.f;
+}
+
+// ---------------------------------------------------------------- small-M linear (time-embedding MLPs)
+// y[m, n] = act_out( b[n] + sum_k W[n,k] * act_in(x[m,k]) ), fp32 activations, bf16 weights, M <= 32.
+// One warp computes 4 output columns for all rows (weights are the traffic; x stays in L1/L2).
+template <int MAXM>
+__global__ void __launch_bounds__(128) linear_small_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ W,
+                                                           const float* __restrict__ bias, float* __restrict__ y, int M,
+                                                           int N, int K, long long ldy, int silu_in, int silu_out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = warp * 4;
+  if (n0 >= N) return;
+  float acc[MAXM][4];
+#pragma unroll
+  for (int m = 0; m < MAXM; ++m)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[m][j] = 0.f;
+  for (int k = lane * 2; k < K; k += 64) {
+    float2 w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = min(n0 + j, N - 1);
+      w[j] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(W + (size_t)n * K + k));
+    }
+#pragma unroll
+    for (int m = 0; m < MAXM; ++m) {
+      if (m < M) {
+        float2 xv = *reinterpret_cast<const float2*>(x + (size_t)m * K + k);
+        if (silu_in) { xv.x = silu(xv.x); xv.y = silu(xv.y); }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[m][j] += xv.x * w[j].x + xv.y * w[j].y;
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < MAXM; ++m)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[m][j] += __shfl_xor_sync(0xffffffffu, acc[m][j], o);
+  if (lane == 0) {
+    for (int m = 0; m < M && m < MAXM; ++m)
+      for (int j = 0; j < 4; ++j)
+        if (n0 + j < N) {
+          float v = acc[m][j] + (bias ? bias[n0 + j] : 0.f);
+          y[(size_t)m * ldy + n0 + j] = silu_out ? silu(v) : v;
+        }
+  }
+}
+
+// ---------------------------------------------------------------- stride-2 3x3 im2col, fp32 NHWC -> bf16 [rows, 9C]
+__global__ void im2col_s2_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int F, int H, int W, int C,
+                                 int Ho, int Wo) {
+  const int c8n = C / 8;
+  const size_t total = (size_t)F * Ho * Wo * 9 * c8n;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(e % c8n);
+    size_t r = e / c8n;
+    const int tap = (int)(r % 9); r /= 9;
+    const int ox = (int)(r % Wo); r /= Wo;
+    const int oy = (int)(r % Ho);
+    const int f = (int)(r / Ho);
+    const int iy = oy * 2 - 1 + tap / 3, ix = ox * 2 - 1 + tap % 3;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+      const float* src = x + (((size_t)f * H + iy) * W + ix) * C + c8 * 8;
+      const float4 a = *reinterpret_cast<const float4*>(src);
+      const float4 b = *reinterpret_cast<const float4*>(src + 4);
+      v = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+    }
+    *reinterpret_cast<uint4*>(out + ((((size_t)f * Ho + oy) * Wo + ox) * 9 + tap) * C + c8 * 8) = v;
+  }
+}
+
+// ---------------------------------------------------------------- CFG + Euler step (sampler)
+// Follows the reference operation order in fp32 (denoiser.py:22-28 with EpsScaling c_skip=1, c_out=-sigma;
+// guiders.py:25-29 + sampling_utils.py:7-9 x_u + s (x_c - x_u); sampling_utils.py:39-40 d = (x - den)/sigma;
+// sampling.py:103-110 x += (sigma_next - sigma) d). eps holds [uncond ; cond] halves. Also emits the next
+// network input x_next * c_in(sigma_next) so the loop needs no extra pass.
+__global__ void cfg_euler_kernel(float* __restrict__ x, const float* __restrict__ eps, float* __restrict__ x_in_next,
+                                 size_t n, float sigma, float sigma_next, float scale, float c_in_next) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const float xv = x[e];
+    const float den_u = eps[e] * (-sigma) + xv;
+    const float den_c = eps[n + e] * (-sigma) + xv;
+    const float den = den_u + scale * (den_c - den_u);
+    const float d = (xv - den) / sigma;
+    const float xn = xv + (sigma_next - sigma) * d;
+    x[e] = xn;
+    if (x_in_next) {
+      const float v = xn * c_in_next;
+      x_in_next[e] = v;
+      x_in_next[n + e] = v;
+    }
+  }
+}
+
+__global__ void scale_dup_kernel(const float* __restrict__ x, float* __restrict__ out, size_t n, float s, int copies) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const float v = x[e] * s;
+    for (int c = 0; c < copies; ++c) out[(size_t)c * n + e] = v;
+  }
+}
+
+static inline int grid_for(size_t total, int threads = 256) {
+  size_t g = (total + threads - 1) / threads;
+  const size_t cap = (size_t)16 * sm_count();
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace pn
+
+using namespace pn;
+
+extern "C" int pn_transpose_f32(const float* in, float* out, int64_t batch, int64_t A, int64_t B, int64_t out_ld,
+                                int64_t out_off, void* stream_v) {
+  PN_REQUIRE(in && out && batch > 0 && A > 0 && B > 0 && out_ld >= out_off + A, "pn_transpose_f32: bad arguments");
+  PN_REQUIRE(batch <= 65535, "pn_transpose_f32: batch too large");
+  dim3 grid((unsigned)((B + 31) / 32), (unsigned)((A + 31) / 32), (unsigned)batch);
+  transpose_kernel<<<grid, dim3(32, 8), 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(in, out, (int)A, (int)B, out_ld,
+                                                                                         (int)out_off);
+  PN_CHECK_CUDA(cudaGetLastError());
+  return PN_OK;
+}
+
+extern "C" int pn_upsample2x_bf16(const float* x, void* y_bf16, int64_t frames, int64_t H, int64_t W, int64_t C,
+                                  void* stream_v) {
+  PN_REQUIRE(x && y_bf16 && frames > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "pn_upsample2x_bf16: bad arguments");
+  const size_t total = (size_t)frames * 4 * H * W * (C / 8);
+  upsample2x_kernel<<<grid_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(
+      x, reinterpret_cast<__nv_bfloat16*>(y_bf16), (int)frames, (int)H, (int)W, (int)C);
+  PN_CHECK_CUDA(cudaGetLastError());
+  return PN_OK;
+}
+
+extern "C" int pn_concat_add(const float* h, const float* skip, const float* ctrl, float* out, int64_t rows, int64_t C1,
+                             int64_t C2, void* stream_v) {
+  PN_REQUIRE(h && skip && out && rows > 0 && C1 % 4 == 0 && C2 % 4 == 0 && C1 > 0 && C2 > 0, "pn_concat_add: bad arguments");
+  const size_t total = (size_t)rows * ((C1 + C2) / 4);
+  concat_add_kernel<<<grid_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(h, skip, ctrl, out, rows,
+                                                                                           (int)C1, (int)C2);
+  PN_CHECK_CUDA(cudaGetLastError());
+  return PN_OK;
+}
+
+extern "C" int pn_add_inplace(float* x, const float* y, int64_t n, void* stream_v) {
+  PN_REQUIRE(x && y && n > 0 && n % 4 == 0, "pn_add_inplace: bad arguments");
+  add_inplace_kernel<<<grid_for((size_t)n / 4), 256, 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(x, y, (size_t)n / 4);
+  PN_CHECK_CUDA(cudaGetLastError());
+  return PN_OK;
+}
+
+extern "C" int pn_cast_bf16(const float* x, void* y_bf16, int64_t n, void* stream_v) {
+  PN_REQUIRE(x && y_bf16 && n > 0 && n % 4 == 0, "pn_cast_bf16: bad arguments");
+  cast_bf16_kernel<<<grid_for((size_t)n / 4), 256, 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(
+      x, reinterpret_cast<__nv_bfloat16*>(y_bf16), (size_t)n / 4);
+  PN_CHECK_CUDA(cudaGetLastError());
+  return PN_OK;
+}
+
+extern "C" int pn_timestep_embedding(const int64_t* t, float* out, int64_t n, int64_t dim, void* stream_v) {
+  PN_REQUIRE(t && out && n > 0 && dim >= 2, "pn_timestep_embedding: bad arguments");
+  const int total = (int)(n * (dim / 2));
+  timestep_embedding_kernel<<<(total + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(
+      reinterpret_cast<const long long*>(t), out, (int)n, (int)dim);
+  PN_CHECK_CUDA(cudaGetLastError());
+  return PN_OK;
+}
+
+extern "C" int pn_linear_small(const float* x, const void* W_bf16, const float* bias, float* y, int64_t M, int64_t N,
+                               int64_t K, int64_t ldy, int silu_in, int silu_out, void* stream_v) {
+  PN_REQUIRE(x && W_bf16 && y, "pn_linear_small: null pointer");
+  PN_REQUIRE(M > 0 && M <= 32 && N > 0 && K > 0 && K % 2 == 0 && ldy >= N, "pn_linear_small: M=%lld N=%lld K=%lld unsupported",
+             (long long)M, (long long)N, (long long)K);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
+  const int warps = (int)((N + 3) / 4);
+  const int blocks = (warps * 32 + 127) / 128;
+  const __nv_bfloat16* W = reinterpret_cast<const __nv_bfloat16*>(W_bf16);
+  if (M <= 8) linear_small_kernel<8><<<blocks, 128, 0, st>>>(x, W, bias, y, (int)M, (int)N, (int)K, ldy, silu_in, silu_out);
+  else if (M <= 16) linear_small_kernel<16><<<blocks, 128, 0, st>>>(x, W, bias, y, (int)M, (int)N, (int)K, ldy, silu_in, silu_out);
+  else linear_small_kernel<32><<<blocks, 128, 0, st>>>(x, W, bias, y, (int)M, (int)N, (int)K, ldy, silu_in, silu_out);
+  PN_CHECK_CUDA(cudaGetLastError());
+  return PN_OK;
+}
+
+extern "C" int pn_im2col3x3_s2(const float* x, void* out_bf16, int64_t frames, int64_t H, int64_t W, int64_t C,
+                               void* stream_v) {
+  PN_REQUIRE(x && out_bf16 && frames > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "pn_im2col3x3_s2: bad arguments");
+  const int Ho = (int)((H + 2 - 3) / 2 + 1), Wo = (int)((W + 2 - 3) / 2 + 1);
+  const size_t total = (size_t)frames * Ho * Wo * 9 * (C / 8);
+  im2col_s2_kernel<<<grid_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(
+      x, reinterpret_cast<__nv_bfloat16*>(out_bf16), (int)frames, (int)H, (int)W, (int)C, Ho, Wo);
+  PN_CHECK_CUDA(cudaGetLastError());
+  return PN_OK;
+}
+
+extern "C" int pn_cfg_euler_step(float* x, const float* eps2, float* x_in_next, int64_t n, float sigma,
+                                 float sigma_next, float cfg_scale, float c_in_next, void* stream_v) {
+  PN_REQUIRE(x && eps2 && n > 0 && sigma > 0.f, "pn_cfg_euler_step: bad arguments");
+  cfg_euler_kernel<<<grid_for((size_t)n), 256, 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(
+      x, eps2, x_in_next, (size_t)n, sigma, sigma_next, cfg_scale, c_in_next);
+  PN_CHECK_CUDA(cudaGetLastError());
+  return PN_OK;
+}
+
+extern "C" int pn_scale_dup(const float* x, float* out, int64_t n, float s, int copies, void* stream_v) {
+  PN_REQUIRE(x && out && n > 0 && copies >= 1, "pn_scale_dup: bad arguments");
+  scale_dup_kernel<<<grid_for((size_t)n), 256, 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(x, out, (size_t)n, s, copies);
+  PN_CHECK_CUDA(cudaGetLastError());
+  return PN_OK;
+}

@@ -1,0 +1,287 @@
+// Normalisation kernels (HBM-bound): they read the fp32 residual stream once and emit the bf16 MMA operand
+// of the GEMM/conv that follows, with the affine transform and SiLU fused in.
+//
+//  * spatial GroupNorm(32)  — statistics over (C/32 channels x all H x Wtot pixels of one frame), i.e. over
+//    ALL SIX VIEWS jointly (reference: util.py:276-283 eps 1e-5 in ResBlock3D, attention.py:129-132 eps 1e-6
+//    in SpatialTemporalTransformer);
+//  * pixel-wise GroupNorm(32) over (C/32 channels x T frames) per pixel (reference: openaimodel.py:509-515,
+//    534-539: GroupNorm applied to the [(b h w), C, T] rearrangement) — here computed in place on the
+//    [b, T, P, C] layout, no rearrange copies;
+//  * LayerNorm(C) per token (attention.py:699-701, eps 1e-5).
+#include "common.cuh"
+#include "ptx.cuh"
+#include "../../include/panacea_b200.h"
+
+namespace pn {
+
+constexpr int GN_GROUPS = 32;
+constexpr int GN_CHUNK = 64;  // pixels per partial-statistics block
+
+// ---------------------------------------------------------------- spatial GN: partial sums per pixel chunk
+// partial[f][chunk][g][2] = (sum, sumsq) over the chunk's pixels x group channels (fp32, <= 64*cpg terms each)
+__global__ void __launch_bounds__(256) gn_partial_kernel(const float* __restrict__ x, float* __restrict__ partial,
+                                                         int P, int C, int nchunks) {
+  __shared__ float bins[GN_GROUPS * 2];
+  const int f = blockIdx.y, chunk = blockIdx.x;
+  const int cpg = C / GN_GROUPS;
+  if (threadIdx.x < GN_GROUPS * 2) bins[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int p0 = chunk * GN_CHUNK;
+  const int p1 = min(P, p0 + GN_CHUNK);
+  const int c4n = C / 4;
+  const float* base = x + ((size_t)f * P) * C;
+  for (int c4 = threadIdx.x; c4 < c4n; c4 += blockDim.x) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int p = p0; p < p1; ++p) {
+      const float4 v = *reinterpret_cast<const float4*>(base + (size_t)p * C + c4 * 4);
+      s[0] += v.x; q[0] += v.x * v.x;
+      s[1] += v.y; q[1] += v.y * v.y;
+      s[2] += v.z; q[2] += v.z * v.z;
+      s[3] += v.w; q[3] += v.w * v.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int g = (c4 * 4 + j) / cpg;
+      atomicAdd(&bins[g * 2], s[j]);
+      atomicAdd(&bins[g * 2 + 1], q[j]);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < GN_GROUPS * 2)
+    partial[((size_t)f * nchunks + chunk) * GN_GROUPS * 2 + threadIdx.x] = bins[threadIdx.x];
+}
+
+// scale[f][c] = rstd*gamma[c]; shift[f][c] = beta[c] - mean*rstd*gamma[c]   (double-precision combine)
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ scale,
+                                   float* __restrict__ shift, int P, int C, int nchunks, float eps) {
+  __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
+  const int f = blockIdx.x;
+  const int cpg = C / GN_GROUPS;
+  if (threadIdx.x < GN_GROUPS) {
+    double s = 0.0, q = 0.0;
+    const float* pp = partial + (size_t)f * nchunks * GN_GROUPS * 2 + threadIdx.x * 2;
+    for (int k = 0; k < nchunks; ++k) {
+      s += (double)pp[(size_t)k * GN_GROUPS * 2];
+      q += (double)pp[(size_t)k * GN_GROUPS * 2 + 1];
+    }
+    const double n = (double)P * cpg;
+    const double mean = s / n;
+    double var = q / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[threadIdx.x] = (float)mean;
+    s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float sc = s_rstd[g] * gamma[c];
+    scale[(size_t)f * C + c] = sc;
+    shift[(size_t)f * C + c] = beta[c] - s_mean[g] * sc;
+  }
+}
+
+// y = act(x*scale[f,c] + shift[f,c]) -> bf16 ; optional raw bf16 copy of x (input of the 1x1 skip conv)
+__global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                                                       const float* __restrict__ shift,
+                                                       __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ raw,
+                                                       int P, int C, int act_silu) {
+  extern __shared__ float sm[];
+  float* s_scale = sm;
+  float* s_shift = sm + C;
+  const int f = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    s_scale[c] = scale[(size_t)f * C + c];
+    s_shift[c] = shift[(size_t)f * C + c];
+  }
+  __syncthreads();
+  const int c8n = C / 8;
+  const size_t total = (size_t)P * c8n;
+  const float* xb = x + (size_t)f * P * C;
+  __nv_bfloat16* yb = y + (size_t)f * P * C;
+  __nv_bfloat16* rb = raw ? raw + (size_t)f * P * C : nullptr;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(e % c8n);
+    const size_t off = (e / c8n) * C + (size_t)c8 * 8;
+    const float4 a = *reinterpret_cast<const float4*>(xb + off);
+    const float4 b = *reinterpret_cast<const float4*>(xb + off + 4);
+    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    if (rb) {
+      *reinterpret_cast<uint4*>(rb + off) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                        pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = v[j] * s_scale[c8 * 8 + j] + s_shift[c8 * 8 + j];
+      v[j] = act_silu ? silu(t) : t;
+    }
+    *reinterpret_cast<uint4*>(yb + off) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                      pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+}
+
+// ---------------------------------------------------------------- pixel-wise temporal GN (+SiLU) -> bf16
+// x: fp32 [b, T, P, C]; one warp per (b, p); lane = group (32 groups); statistics over T x cpg values.
+__global__ void __launch_bounds__(256) gn_pixel_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
+                                                       int nb, int T, int P, int C, float eps, int act_silu) {
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp_global >= nb * P) return;
+  const int b = warp_global / P, p = warp_global - b * P;
+  const int cpg = C / GN_GROUPS;  // even (C % 64 == 0)
+  const size_t frame_stride = (size_t)P * C;
+  const float* x0 = x + ((size_t)b * T * P + p) * C + lane * cpg;
+  __nv_bfloat16* y0 = y + ((size_t)b * T * P + p) * C + lane * cpg;
+  // shifted single-pass moments (shift = first element of the group) for conditioning
+  const float K = x0[0];
+  float s = 0.f, q = 0.f;
+  for (int t = 0; t < T; ++t) {
+    const float2* r = reinterpret_cast<const float2*>(x0 + t * frame_stride);
+    for (int j = 0; j < cpg / 2; ++j) {
+      const float2 v = r[j];
+      const float d0 = v.x - K, d1 = v.y - K;
+      s += d0 + d1;
+      q += d0 * d0 + d1 * d1;
+    }
+  }
+  const float n = (float)(T * cpg);
+  const float dm = s / n;
+  const float mean = K + dm;
+  const float var = fmaxf(q / n - dm * dm, 0.f);
+  const float rstd = rsqrtf(var + eps);
+  for (int t = 0; t < T; ++t) {
+    const float2* r = reinterpret_cast<const float2*>(x0 + t * frame_stride);
+    uint32_t* w = reinterpret_cast<uint32_t*>(y0 + t * frame_stride);
+    for (int j = 0; j < cpg / 2; ++j) {
+      const float2 v = r[j];
+      const int c = lane * cpg + 2 * j;
+      float a0 = (v.x - mean) * rstd * gamma[c] + beta[c];
+      float a1 = (v.y - mean) * rstd * gamma[c + 1] + beta[c + 1];
+      if (act_silu) { a0 = silu(a0); a1 = silu(a1); }
+      w[j] = pack_bf16x2(a0, a1);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- LayerNorm per token -> bf16
+// one warp per row; the row (C <= 2048 floats) lives in registers between the two passes.
+template <int MAXV>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
+                                                        long long rows, int C, float eps) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * C);
+  const int n4 = C / 4;
+  float4 v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int j = lane + i * 32;
+    if (j < n4) {
+      v[i] = xr[j];
+      s += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int j = lane + i * 32;
+    if (j < n4) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += a * a + b * b + c * c + d * d;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / (float)C + eps);
+  uint2* yr = reinterpret_cast<uint2*>(y + row * C);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int j = lane + i * 32;
+    if (j < n4) {
+      const float4 g = g4[j], bb = b4[j];
+      const float o0 = (v[i].x - mean) * rstd * g.x + bb.x;
+      const float o1 = (v[i].y - mean) * rstd * g.y + bb.y;
+      const float o2 = (v[i].z - mean) * rstd * g.z + bb.z;
+      const float o3 = (v[i].w - mean) * rstd * g.w + bb.w;
+      yr[j] = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+    }
+  }
+}
+
+}  // namespace pn
+
+using namespace pn;
+
+extern "C" int64_t pn_groupnorm_workspace_floats(int64_t frames, int64_t pixels, int64_t channels) {
+  const int64_t nchunks = (pixels + GN_CHUNK - 1) / GN_CHUNK;
+  return frames * nchunks * GN_GROUPS * 2 + 2 * frames * channels;
+}
+
+extern "C" int pn_groupnorm_silu(const float* x, const float* gamma, const float* beta, void* y_bf16,
+                                 void* raw_bf16, float* workspace, int64_t frames, int64_t pixels,
+                                 int64_t channels, float eps, int act_silu, void* stream_v) {
+  PN_REQUIRE(x && gamma && beta && y_bf16 && workspace, "pn_groupnorm_silu: null pointer");
+  PN_REQUIRE(channels % 32 == 0 && channels % 8 == 0 && channels <= 8192, "pn_groupnorm_silu: C=%lld unsupported",
+             (long long)channels);
+  PN_REQUIRE(frames > 0 && pixels > 0, "pn_groupnorm_silu: empty input");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
+  const int P = (int)pixels, C = (int)channels, F = (int)frames;
+  const int nchunks = (P + GN_CHUNK - 1) / GN_CHUNK;
+  float* partial = workspace;
+  float* scale = workspace + (size_t)F * nchunks * GN_GROUPS * 2;
+  float* shift = scale + (size_t)F * C;
+  gn_partial_kernel<<<dim3(nchunks, F), 256, 0, st>>>(x, partial, P, C, nchunks);
+  PN_CHECK_CUDA(cudaGetLastError());
+  gn_finalize_kernel<<<F, 256, 0, st>>>(partial, gamma, beta, scale, shift, P, C, nchunks, eps);
+  PN_CHECK_CUDA(cudaGetLastError());
+  const size_t total = (size_t)P * (C / 8);
+  int gx = (int)((total + 255) / 256);
+  const int cap = 8 * sm_count() / (F > 0 ? 1 : 1);
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  gn_apply_kernel<<<dim3(gx, F), 256, 2 * C * sizeof(float), st>>>(
+      x, scale, shift, reinterpret_cast<__nv_bfloat16*>(y_bf16), reinterpret_cast<__nv_bfloat16*>(raw_bf16), P, C,
+      act_silu);
+  PN_CHECK_CUDA(cudaGetLastError());
+  return PN_OK;
+}
+
+extern "C" int pn_groupnorm_pixel_silu(const float* x, const float* gamma, const float* beta, void* y_bf16,
+                                       int64_t batch, int64_t frames_per_seq, int64_t pixels, int64_t channels,
+                                       float eps, int act_silu, void* stream_v) {
+  PN_REQUIRE(x && gamma && beta && y_bf16, "pn_groupnorm_pixel_silu: null pointer");
+  PN_REQUIRE(channels % 64 == 0, "pn_groupnorm_pixel_silu: C=%lld must be a multiple of 64", (long long)channels);
+  PN_REQUIRE(batch > 0 && frames_per_seq > 0 && pixels > 0, "pn_groupnorm_pixel_silu: empty input");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
+  const long long warps = batch * pixels;
+  const int blocks = (int)((warps * 32 + 255) / 256);
+  gn_pixel_kernel<<<blocks, 256, 0, st>>>(x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y_bf16), (int)batch,
+                                          (int)frames_per_seq, (int)pixels, (int)channels, eps, act_silu);
+  PN_CHECK_CUDA(cudaGetLastError());
+  return PN_OK;
+}
+
+extern "C" int pn_layernorm(const float* x, const float* gamma, const float* beta, void* y_bf16, int64_t rows,
+                            int64_t channels, float eps, void* stream_v) {
+  PN_REQUIRE(x && gamma && beta && y_bf16, "pn_layernorm: null pointer");
+  PN_REQUIRE(channels % 4 == 0 && channels <= 2048 && channels > 0, "pn_layernorm: C=%lld unsupported", (long long)channels);
+  PN_REQUIRE(rows > 0, "pn_layernorm: empty input");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
+  const long long blocks = (rows * 32 + 255) / 256;
+  __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(y_bf16);
+  const int C = (int)channels;
+  if (C <= 512) layernorm_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, beta, y, rows, C, eps);
+  else if (C <= 1024) layernorm_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, beta, y, rows, C, eps);
+  else layernorm_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, beta, y, rows, C, eps);
+  PN_CHECK_CUDA(cudaGetLastError());
+  return PN_OK;
+}

@@ -104,3 +104,202 @@ class NativeOps:
         _lib.check(self.lib.pn_gemm(C.byref(args), _stream()), "pn_gemm")
         self.launches += 1
         return out.reshape(*lead, n_out) if out.is_contiguous() else out
+
+    # ------------------------------------------------------------------ normalisation
+    def groupnorm(self, x, gamma, beta, eps, silu, want_raw=False):
+        """x fp32 [F, P, C] (or [F,H,W,C]) -> bf16 same shape; statistics over (C/32, all pixels of a frame)."""
+        _req(x.is_cuda and x.dtype == F32 and x.is_contiguous(), "groupnorm: x must be contiguous CUDA fp32")
+        Fr, Cc = x.shape[0], x.shape[-1]
+        P = x.numel() // (Fr * Cc)
+        y = torch.empty(x.shape, device=x.device, dtype=BF16)
+        raw = torch.empty(x.shape, device=x.device, dtype=BF16) if want_raw else None
+        nws = self.lib.pn_groupnorm_workspace_floats(Fr, P, Cc)
+        ws = torch.empty(nws, device=x.device, dtype=F32)
+        _lib.check(self.lib.pn_groupnorm_silu(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(raw), _ptr(ws), Fr, P, Cc,
+                                             float(eps), int(bool(silu)), _stream()), "pn_groupnorm_silu")
+        self.launches += 3
+        return (y, raw) if want_raw else y
+
+    def groupnorm_pixel(self, x, gamma, beta, eps, silu):
+        """x fp32 [b, T, P, C] -> bf16; statistics over (C/32, T) per pixel (temporal branch of ResBlock3D)."""
+        _req(x.is_cuda and x.dtype == F32 and x.is_contiguous() and x.dim() == 4, "groupnorm_pixel: x fp32 [b,T,P,C]")
+        b, T, P, Cc = x.shape
+        y = torch.empty(x.shape, device=x.device, dtype=BF16)
+        _lib.check(self.lib.pn_groupnorm_pixel_silu(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), b, T, P, Cc, float(eps),
+                                                   int(bool(silu)), _stream()), "pn_groupnorm_pixel_silu")
+        self.launches += 1
+        return y
+
+    def layernorm(self, x, gamma, beta, eps=1e-5):
+        _req(x.is_cuda and x.dtype == F32 and x.is_contiguous(), "layernorm: x must be contiguous CUDA fp32")
+        Cc = x.shape[-1]
+        rows = x.numel() // Cc
+        y = torch.empty(x.shape, device=x.device, dtype=BF16)
+        _lib.check(self.lib.pn_layernorm(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), rows, Cc, float(eps), _stream()),
+                   "pn_layernorm")
+        self.launches += 1
+        return y
+
+    # ------------------------------------------------------------------ attention
+    def _attention(self, q, k, v, out, *, q_ld, kv_ld, out_ld, F, H, V, W, Hk, Vk, Wk, kv_frame_div, heads, views):
+        a = _lib.AttnArgs()
+        a.q, a.k, a.v, a.out = q, k, v, out
+        a.q_ld, a.kv_ld, a.out_ld = q_ld, kv_ld, out_ld
+        a.F, a.H, a.V, a.W = F, H, V, W
+        a.Hk, a.Vk, a.Wk = Hk, Vk, Wk
+        a.kv_frame_div = kv_frame_div
+        a.heads, a.head_dim = heads, 64
+        for vi, lst in enumerate(views):
+            a.kv_view_count[vi] = len(lst)
+            for j, kvv in enumerate(lst):
+                a.kv_views[vi][j] = kvv
+        a.scale = 64 ** -0.5
+        _lib.check(self.lib.pn_attention(C.byref(a), _stream()), "pn_attention")
+        self.launches += 1
+
+    def attention_view(self, qkv, heads, cross, neighbours):
+        """qkv bf16 [F, H, V, w, 3C] (fused q|k|v channels) -> bf16 [F, H, V, w, C].
+        cross=False: each view attends itself; cross=True: view v attends neighbours[v]."""
+        _req(qkv.is_cuda and qkv.dtype == BF16 and qkv.is_contiguous() and qkv.dim() == 5, "attention_view: qkv bf16 [F,H,V,w,3C]")
+        Fr, H, V, w, C3 = qkv.shape
+        Cc = C3 // 3
+        _req(Cc == heads * 64, "attention_view: head_dim must be 64")
+        out = torch.empty((Fr, H, V, w, Cc), device=qkv.device, dtype=BF16)
+        views = [list(neighbours[v]) for v in range(V)] if cross else [[v] for v in range(V)]
+        base = qkv.data_ptr()
+        self._attention(base, base + 2 * Cc, base + 4 * Cc, out.data_ptr(), q_ld=C3, kv_ld=C3, out_ld=Cc, F=Fr, H=H, V=V, W=w,
+                        Hk=H, Vk=V, Wk=w, kv_frame_div=1, heads=heads, views=views)
+        return out
+
+    def attention_text(self, q, kv, heads):
+        """q bf16 [b, Nq, C]; kv bf16 [b, Nk, 2C] (k | v channels), Nk <= 128 -> bf16 [b, Nq, C]."""
+        _req(q.is_cuda and q.dtype == BF16 and q.is_contiguous() and kv.dtype == BF16 and kv.is_contiguous(), "attention_text: bf16 contiguous")
+        b, Nq, Cc = q.shape
+        Nk = kv.shape[1]
+        _req(kv.shape[0] == b and kv.shape[2] == 2 * Cc and Cc == heads * 64 and Nk <= 128, "attention_text: bad shapes")
+        out = torch.empty_like(q)
+        base = kv.data_ptr()
+        self._attention(q.data_ptr(), base, base + 2 * Cc, out.data_ptr(), q_ld=Cc, kv_ld=2 * Cc, out_ld=Cc, F=b, H=1, V=1,
+                        W=Nq, Hk=1, Vk=1, Wk=Nk, kv_frame_div=1, heads=heads, views=[[0]])
+        return out
+
+    def attention_temporal(self, qkv, heads):
+        """qkv bf16 [b, T, P, 3C] -> bf16 [b, T, P, C]; softmax over the T frames of each pixel."""
+        _req(qkv.is_cuda and qkv.dtype == BF16 and qkv.is_contiguous() and qkv.dim() == 4, "attention_temporal: qkv bf16 [b,T,P,3C]")
+        b, T, P, C3 = qkv.shape
+        Cc = C3 // 3
+        _req(Cc == heads * 64, "attention_temporal: head_dim must be 64")
+        out = torch.empty((b, T, P, Cc), device=qkv.device, dtype=BF16)
+        base = qkv.data_ptr()
+        _lib.check(self.lib.pn_attention_temporal(base, base + 2 * Cc, base + 4 * Cc, out.data_ptr(), b, T, P, heads, 64, C3, Cc,
+                                                 64 ** -0.5, _stream()), "pn_attention_temporal")
+        self.launches += 1
+        return out
+
+    # ------------------------------------------------------------------ small convs / layout / sampler helpers
+    def conv3x3_direct(self, x, w_packed, bias, cout, *, stride=1, silu=False, addend=None, out_dtype=F32):
+        """x fp32|bf16 [F,H,W,Cin] channels-last; w_packed fp32 [9, Cin, Cout_pad]; -> [F,Ho,Wo,cout]."""
+        _req(x.is_cuda and x.is_contiguous() and x.dim() == 4 and x.dtype in (F32, BF16), "conv3x3_direct: x [F,H,W,Cin]")
+        Fr, H, W, Cin = x.shape
+        _req(w_packed.dtype == F32 and w_packed.is_contiguous() and w_packed.shape[0] == 9 and w_packed.shape[1] == Cin,
+             "conv3x3_direct: w_packed fp32 [9,Cin,Cout_pad]")
+        cpad = w_packed.shape[2]
+        Ho, Wo = (H + 2 - 3) // stride + 1, (W + 2 - 3) // stride + 1
+        y = torch.empty((Fr, Ho, Wo, cout), device=x.device, dtype=out_dtype)
+        yf = _ptr(y) if out_dtype == F32 else None
+        yb = _ptr(y) if out_dtype == BF16 else None
+        _lib.check(self.lib.pn_conv3x3_direct(_ptr(x), int(x.dtype == BF16), _ptr(w_packed), _ptr(bias), _ptr(addend), yf, yb,
+                                             Fr, H, W, Cin, cout, cpad, stride, int(bool(silu)), _stream()), "pn_conv3x3_direct")
+        self.launches += 1
+        return y
+
+    def im2col_s2(self, x):
+        _req(x.is_cuda and x.dtype == F32 and x.is_contiguous() and x.dim() == 4, "im2col_s2: x fp32 [F,H,W,C]")
+        Fr, H, W, Cc = x.shape
+        Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        out = torch.empty((Fr * Ho * Wo, 9 * Cc), device=x.device, dtype=BF16)
+        _lib.check(self.lib.pn_im2col3x3_s2(_ptr(x), _ptr(out), Fr, H, W, Cc, _stream()), "pn_im2col3x3_s2")
+        self.launches += 1
+        return out, (Fr, Ho, Wo)
+
+    def upsample2x(self, x):
+        _req(x.is_cuda and x.dtype == F32 and x.is_contiguous() and x.dim() == 4, "upsample2x: x fp32 [F,H,W,C]")
+        Fr, H, W, Cc = x.shape
+        y = torch.empty((Fr, 2 * H, 2 * W, Cc), device=x.device, dtype=BF16)
+        _lib.check(self.lib.pn_upsample2x_bf16(_ptr(x), _ptr(y), Fr, H, W, Cc, _stream()), "pn_upsample2x_bf16")
+        self.launches += 1
+        return y
+
+    def concat_add(self, h, skip, ctrl):
+        _req(h.dtype == F32 and skip.dtype == F32 and h.is_contiguous() and skip.is_contiguous(), "concat_add: fp32 contiguous")
+        C1, C2 = h.shape[-1], skip.shape[-1]
+        rows = h.numel() // C1
+        _req(skip.numel() // C2 == rows, "concat_add: row mismatch")
+        out = torch.empty((*h.shape[:-1], C1 + C2), device=h.device, dtype=F32)
+        _lib.check(self.lib.pn_concat_add(_ptr(h), _ptr(skip), _ptr(ctrl), _ptr(out), rows, C1, C2, _stream()), "pn_concat_add")
+        self.launches += 1
+        return out
+
+    def add_(self, x, y):
+        _req(x.dtype == F32 and y.dtype == F32 and x.is_contiguous() and y.is_contiguous() and x.numel() == y.numel(), "add_: fp32 same size")
+        _lib.check(self.lib.pn_add_inplace(_ptr(x), _ptr(y), x.numel(), _stream()), "pn_add_inplace")
+        self.launches += 1
+        return x
+
+    def cast_bf16(self, x):
+        _req(x.dtype == F32 and x.is_contiguous(), "cast_bf16: fp32 contiguous")
+        y = torch.empty(x.shape, device=x.device, dtype=BF16)
+        _lib.check(self.lib.pn_cast_bf16(_ptr(x), _ptr(y), x.numel(), _stream()), "pn_cast_bf16")
+        self.launches += 1
+        return y
+
+    def nchw_to_nhwc(self, x, out=None, ch_off=0):
+        """x fp32 [F,C,H,W] -> out[F,H,W,ch_off:ch_off+C] (out may be wider: channel concat)."""
+        _req(x.is_cuda and x.dtype == F32 and x.is_contiguous() and x.dim() == 4, "nchw_to_nhwc: x fp32 [F,C,H,W]")
+        Fr, Cc, H, W = x.shape
+        if out is None:
+            out = torch.empty((Fr, H, W, Cc), device=x.device, dtype=F32)
+        _lib.check(self.lib.pn_transpose_f32(_ptr(x), _ptr(out), Fr, Cc, H * W, out.shape[-1], ch_off, _stream()), "pn_transpose_f32")
+        self.launches += 1
+        return out
+
+    def nhwc_to_nchw(self, x):
+        _req(x.is_cuda and x.dtype == F32 and x.is_contiguous() and x.dim() == 4, "nhwc_to_nchw: x fp32 [F,H,W,C]")
+        Fr, H, W, Cc = x.shape
+        out = torch.empty((Fr, Cc, H, W), device=x.device, dtype=F32)
+        _lib.check(self.lib.pn_transpose_f32(_ptr(x), _ptr(out), Fr, H * W, Cc, H * W, 0, _stream()), "pn_transpose_f32")
+        self.launches += 1
+        return out
+
+    def timestep_embedding(self, t, dim):
+        _req(t.is_cuda and t.dtype == torch.int64 and t.is_contiguous(), "timestep_embedding: t must be CUDA int64")
+        out = torch.empty((t.numel(), dim), device=t.device, dtype=F32)
+        _lib.check(self.lib.pn_timestep_embedding(_ptr(t), _ptr(out), t.numel(), dim, _stream()), "pn_timestep_embedding")
+        self.launches += 1
+        return out
+
+    def linear_small(self, x, w, bias, silu_in=False, silu_out=False):
+        """x fp32 [M<=32, K]; w bf16 [N, K]; -> fp32 [M, N]."""
+        _req(x.dtype == F32 and x.is_contiguous() and w.dtype == BF16 and w.is_contiguous(), "linear_small: dtypes")
+        M, K = x.shape
+        N = w.shape[0]
+        y = torch.empty((M, N), device=x.device, dtype=F32)
+        _lib.check(self.lib.pn_linear_small(_ptr(x), _ptr(w), _ptr(bias), _ptr(y), M, N, K, N, int(silu_in), int(silu_out),
+                                           _stream()), "pn_linear_small")
+        self.launches += 1
+        return y
+
+    def cfg_euler_step(self, x, eps2, x_in_next, sigma, sigma_next, scale, c_in_next):
+        _req(x.dtype == F32 and eps2.dtype == F32 and x.is_contiguous() and eps2.is_contiguous() and eps2.numel() == 2 * x.numel(),
+             "cfg_euler_step: shapes")
+        _lib.check(self.lib.pn_cfg_euler_step(_ptr(x), _ptr(eps2), _ptr(x_in_next), x.numel(), float(sigma), float(sigma_next),
+                                             float(scale), float(c_in_next), _stream()), "pn_cfg_euler_step")
+        self.launches += 1
+        return x
+
+    def scale_dup(self, x, s, copies):
+        _req(x.dtype == F32 and x.is_contiguous(), "scale_dup: fp32 contiguous")
+        out = torch.empty((copies * x.shape[0], *x.shape[1:]), device=x.device, dtype=F32)
+        _lib.check(self.lib.pn_scale_dup(_ptr(x), _ptr(out), x.numel(), float(s), copies, _stream()), "pn_scale_dup")
+        self.launches += 1
+        return out
