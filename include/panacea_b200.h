@@ -44,7 +44,7 @@ int pn_abi_version(void);
  *   out[row, n] = epi( sum_{th,tw,c} A[nb, y+th-taps_h/2, x+tw-taps_w/2, c] * B[n, (th*taps_w+tw)*C + c] )
  * with zero padding outside [0,H)x[0,W) and row = (nb*H + y)*W + x.
  * epi: + bias[n] + rowvec[(row / rows_per_group) % n_groups, n]; GEGLU (interleaved value/gate columns ->
- * N/2 outputs, attention.py:91-99); + residual[row, n] (fp32); store fp32 or bf16.
+ * N/2 outputs, attention.py:91-99); + residual[row, n] + residual2[row, n] (fp32); store fp32 or bf16.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct pn_gemm_args {
   const void* A;          /* bf16 [NB, H, W, C] with element strides below (C contiguous) */
@@ -53,9 +53,11 @@ typedef struct pn_gemm_args {
   const float* bias;      /* [N] or NULL */
   const float* rowvec;    /* [n_groups, N] or NULL */
   const float* residual;  /* fp32 [NB*H*W, ldr] or NULL (may alias out when both fp32) */
+  const float* residual2; /* second fp32 addend [NB*H*W, ldr2] or NULL (fp32 output only) */
   int64_t NB, H, W, C;
   int64_t a_stride_w, a_stride_h, a_stride_n; /* elements */
-  int64_t ldo, ldr;
+  int64_t ldo, ldr, ldr2;
+  int64_t rowvec_ld;      /* row stride of rowvec in elements (0 = N) */
   int32_t N;
   int32_t taps_h, taps_w;
   int32_t rows_per_group, n_groups;

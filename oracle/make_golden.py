@@ -32,7 +32,7 @@ def golden_eps(case: Cs.EpsCase) -> dict:
     with R.view_height_shim(case.H, case.w):
         eps = model(x, t, dict(c))
     dt = time.time() - t0
-    return {"meta": case.meta(), "eps": eps.contiguous(), "seconds": dt, "torch": torch.__version__,
+    return {"meta": case.meta(), "eps": eps.contiguous(), "seconds": dt, "torch": str(torch.__version__),
             "threads": torch.get_num_threads()}
 
 

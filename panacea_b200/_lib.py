@@ -21,10 +21,10 @@ class PanaceaNativeError(RuntimeError):
 class GemmArgs(C.Structure):
     _fields_ = [
         ("A", C.c_void_p), ("B", C.c_void_p), ("out", C.c_void_p),
-        ("bias", C.c_void_p), ("rowvec", C.c_void_p), ("residual", C.c_void_p),
+        ("bias", C.c_void_p), ("rowvec", C.c_void_p), ("residual", C.c_void_p), ("residual2", C.c_void_p),
         ("NB", C.c_int64), ("H", C.c_int64), ("W", C.c_int64), ("C", C.c_int64),
         ("a_stride_w", C.c_int64), ("a_stride_h", C.c_int64), ("a_stride_n", C.c_int64),
-        ("ldo", C.c_int64), ("ldr", C.c_int64),
+        ("ldo", C.c_int64), ("ldr", C.c_int64), ("ldr2", C.c_int64), ("rowvec_ld", C.c_int64),
         ("N", C.c_int32), ("taps_h", C.c_int32), ("taps_w", C.c_int32),
         ("rows_per_group", C.c_int32), ("n_groups", C.c_int32),
         ("out_bf16", C.c_int32), ("geglu", C.c_int32),

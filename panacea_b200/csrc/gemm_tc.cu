@@ -41,7 +41,8 @@ struct GemmParams {
   const float* bias;
   const float* rowvec;
   const float* residual;
-  long long ldo, ldr;
+  const float* residual2;
+  long long ldo, ldr, ldr2, ldv;
   int rows_per_group, n_groups;
   int out_bf16;
   int geglu;
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             if (n0 + j < p.N) f[j] += __ldg(p.bias + n0 + j);
         }
         if (p.rowvec != nullptr && my_row >= 0) {
-          const float* rv = p.rowvec + (long long)((my_row / p.rows_per_group) % p.n_groups) * p.N;
+          const float* rv = p.rowvec + (long long)((my_row / p.rows_per_group) % p.n_groups) * p.ldv;
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (n0 + j < p.N) f[j] += __ldg(rv + n0 + j);
@@ -293,6 +294,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 const float4 r = *reinterpret_cast<const float4*>(p.residual + (long long)grow * p.ldr + n0 + ch * 4);
                 val.x += r.x; val.y += r.y; val.z += r.z; val.w += r.w;
               }
+              if (p.residual2 != nullptr) {
+                const float4 r = *reinterpret_cast<const float4*>(p.residual2 + (long long)grow * p.ldr2 + n0 + ch * 4);
+                val.x += r.x; val.y += r.y; val.z += r.z; val.w += r.w;
+              }
               *reinterpret_cast<float4*>(out + (long long)grow * p.ldo + n0 + ch * 4) = val;
             }
           }
@@ -364,6 +369,7 @@ extern "C" int pn_gemm(const pn_gemm_args* a, void* stream_v) {
   PN_REQUIRE(a->ldo >= n_out && a->ldo % 8 == 0, "pn_gemm: ldo=%lld too small or misaligned", (long long)a->ldo);
   if (a->geglu) PN_REQUIRE(a->out_bf16 && a->residual == nullptr && a->N % 32 == 0, "pn_gemm: GEGLU needs bf16 out, no residual, N%%32==0");
   if (a->residual) PN_REQUIRE(a->ldr >= a->N && a->ldr % 4 == 0, "pn_gemm: bad ldr");
+  if (a->residual2) PN_REQUIRE(!a->out_bf16 && !a->geglu && a->ldr2 >= a->N && a->ldr2 % 4 == 0, "pn_gemm: residual2 needs fp32 out and a valid ldr2");
   if (a->rowvec) PN_REQUIRE(a->rows_per_group > 0 && a->n_groups > 0, "pn_gemm: rowvec needs rows_per_group/n_groups");
 
   GemmParams p;
@@ -386,7 +392,9 @@ extern "C" int pn_gemm(const pn_gemm_args* a, void* stream_v) {
   p.pad_h = a->taps_h / 2; p.pad_w = a->taps_w / 2;
   p.N = a->N;
   p.out = a->out; p.bias = a->bias; p.rowvec = a->rowvec; p.residual = a->residual;
-  p.ldo = a->ldo; p.ldr = a->ldr;
+  p.residual2 = a->residual2;
+  p.ldo = a->ldo; p.ldr = a->ldr; p.ldr2 = a->ldr2;
+  p.ldv = a->rowvec_ld > 0 ? a->rowvec_ld : a->N;
   p.rows_per_group = a->rows_per_group > 0 ? a->rows_per_group : 1;
   p.n_groups = a->n_groups > 0 ? a->n_groups : 1;
   p.out_bf16 = a->out_bf16; p.geglu = a->geglu;

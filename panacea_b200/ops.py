@@ -36,7 +36,7 @@ class NativeOps:
         self.launches = 0
 
     # ------------------------------------------------------------------ GEMM / implicit conv
-    def gemm(self, a, w, *, bias=None, rowvec=None, rows_per_group=0, n_groups=0, residual=None,
+    def gemm(self, a, w, *, bias=None, rowvec=None, rows_per_group=0, n_groups=0, residual=None, residual2=None,
              geglu=False, out_dtype=F32, taps=(1, 1), out=None):
         """out[row, :] = epi(sum_taps A[shifted pixel] @ w^T). See include/panacea_b200.h::pn_gemm.
 
@@ -88,12 +88,18 @@ class NativeOps:
         if bias is not None:
             _req(bias.dtype == F32 and bias.numel() == N, "gemm: bias must be fp32 [N]")
         if rowvec is not None:
-            _req(rowvec.dtype == F32 and rowvec.is_contiguous() and rowvec.shape[-1] == N, "gemm: rowvec fp32 [G,N]")
-            _req(rows_per_group > 0 and n_groups > 0 and rowvec.numel() == n_groups * N, "gemm: rowvec groups")
+            _req(rowvec.dtype == F32 and rowvec.dim() == 2 and rowvec.stride(1) == 1 and rowvec.shape[1] == N,
+                 "gemm: rowvec fp32 [G,N] (rows may be strided)")
+            _req(rows_per_group > 0 and n_groups > 0 and rowvec.shape[0] == n_groups, "gemm: rowvec groups")
+            args.rowvec_ld = rowvec.stride(0)
         if residual is not None:
             _req(residual.dtype == F32 and residual.stride(-1) == 1, "gemm: residual must be fp32")
             r2 = residual.reshape(rows, -1) if residual.is_contiguous() else residual
             args.ldr = r2.stride(0)
+        if residual2 is not None:
+            _req(residual2.dtype == F32 and residual2.is_contiguous() and out_dtype == F32, "gemm: residual2 must be fp32")
+            args.residual2 = residual2.data_ptr()
+            args.ldr2 = residual2.numel() // rows
         args.NB, args.H, args.W, args.C = NB, H, W, Cc
         args.a_stride_w, args.a_stride_h, args.a_stride_n = sw, sh, sn
         args.ldo = out2.stride(0)

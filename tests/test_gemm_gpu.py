@@ -5,6 +5,10 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
+# the torch references below must be true fp32 (cuDNN/cuBLAS default to TF32 for conv/matmul on this GPU)
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
 
 @pytest.fixture(scope="module")
 def ops():

@@ -1,0 +1,173 @@
+"""TEST INFRASTRUCTURE — a plain-torch op set with the same interface as panacea_b200.ops.NativeOps.
+
+It exists so that the host-side orchestration (panacea_b200/engine.py: packing, layouts, epilogue fusion
+bookkeeping, view/neighbour tables, caching) can be checked on CPU, without a GPU, against the oracle and the
+reference's golden outputs. It is never imported by the package: the product path has no fallback.
+Semantics follow include/panacea_b200.h literally (channels-last, fused epilogues).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+F32 = torch.float32
+
+
+class TorchRefOps:
+    def __init__(self):
+        self.launches = 0
+
+    def gemm(self, a, w, *, bias=None, rowvec=None, rows_per_group=0, n_groups=0, residual=None, residual2=None,
+             geglu=False, out_dtype=F32, taps=(1, 1), out=None):
+        th, tw = taps
+        C = a.shape[-1]
+        N = w.shape[0]
+        wf = w.float()
+        if (th, tw) == (1, 1):
+            lead = a.shape[:-1]
+            y = a.float().reshape(-1, C) @ wf.t()
+        else:
+            NB, H, W, _ = a.shape
+            lead = (NB, H, W)
+            ap = F.pad(a.float(), (0, 0, tw // 2, tw // 2, th // 2, th // 2))
+            y = torch.zeros(NB * H * W, N)
+            for i in range(th):
+                for j in range(tw):
+                    tap = i * tw + j
+                    y += ap[:, i:i + H, j:j + W, :].reshape(-1, C) @ wf[:, tap * C:(tap + 1) * C].t()
+        rows = y.shape[0]
+        if bias is not None:
+            y = y + bias
+        if rowvec is not None:
+            grp = (torch.arange(rows) // rows_per_group) % n_groups
+            y = y + rowvec[grp]
+        if geglu:
+            y = y[:, 0::2] * F.gelu(y[:, 1::2])
+        if residual is not None:
+            y = y + residual.reshape(rows, -1)
+        if residual2 is not None:
+            y = y + residual2.reshape(rows, -1)
+        y = y.to(out_dtype)
+        if out is not None:
+            out.reshape(rows, -1).copy_(y)
+            return out.reshape(*lead, y.shape[1])
+        return y.reshape(*lead, y.shape[1])
+
+    def groupnorm(self, x, gamma, beta, eps, silu, want_raw=False):
+        Fr, C = x.shape[0], x.shape[-1]
+        z = x.reshape(Fr, -1, C).permute(0, 2, 1)
+        y = F.group_norm(z, 32, gamma, beta, eps)
+        if silu:
+            y = F.silu(y)
+        y = y.permute(0, 2, 1).reshape(x.shape).contiguous()
+        return (y, x.clone()) if want_raw else y
+
+    def groupnorm_pixel(self, x, gamma, beta, eps, silu):
+        b, T, P, C = x.shape
+        z = x.permute(0, 2, 3, 1).reshape(b * P, C, T)
+        y = F.group_norm(z, 32, gamma, beta, eps)
+        if silu:
+            y = F.silu(y)
+        return y.reshape(b, P, C, T).permute(0, 3, 1, 2).contiguous()
+
+    def layernorm(self, x, gamma, beta, eps=1e-5):
+        return F.layer_norm(x, (x.shape[-1],), gamma, beta, eps)
+
+    @staticmethod
+    def _mha(q, k, v, heads):
+        B, Nq, C = q.shape
+        d = C // heads
+        qh = q.reshape(B, Nq, heads, d).transpose(1, 2)
+        kh = k.reshape(B, -1, heads, d).transpose(1, 2)
+        vh = v.reshape(B, -1, heads, d).transpose(1, 2)
+        s = (qh @ kh.transpose(-1, -2)) * (d ** -0.5)
+        return (s.softmax(-1) @ vh).transpose(1, 2).reshape(B, Nq, C)
+
+    def attention_view(self, qkv, heads, cross, neighbours):
+        Fr, H, V, w, C3 = qkv.shape
+        C = C3 // 3
+        q, k, v = qkv.float().split(C, dim=-1)
+        out = torch.empty(Fr, H, V, w, C)
+        for i in range(V):
+            nb = neighbours[i] if cross else (i,)
+            ki = torch.cat([k[:, :, j] for j in nb], dim=2).reshape(Fr, -1, C)
+            vi = torch.cat([v[:, :, j] for j in nb], dim=2).reshape(Fr, -1, C)
+            out[:, :, i] = self._mha(q[:, :, i].reshape(Fr, H * w, C), ki, vi, heads).reshape(Fr, H, w, C)
+        return out.to(qkv.dtype)
+
+    def attention_text(self, q, kv, heads):
+        C = q.shape[-1]
+        return self._mha(q.float(), kv.float()[..., :C], kv.float()[..., C:], heads).to(q.dtype)
+
+    def attention_temporal(self, qkv, heads):
+        b, T, P, C3 = qkv.shape
+        C = C3 // 3
+        q, k, v = qkv.float().split(C, dim=-1)
+        seq = lambda z: z.permute(0, 2, 1, 3).reshape(b * P, T, C)
+        o = self._mha(seq(q), seq(k), seq(v), heads)
+        return o.reshape(b, P, T, C).permute(0, 2, 1, 3).contiguous().to(qkv.dtype)
+
+    def conv3x3_direct(self, x, w_packed, bias, cout, *, stride=1, silu=False, addend=None, out_dtype=F32):
+        cin = x.shape[-1]
+        w = w_packed[:, :cin, :cout].reshape(3, 3, cin, cout).permute(3, 2, 0, 1)
+        y = F.conv2d(x.float().permute(0, 3, 1, 2), w, bias, stride=stride, padding=1)
+        if silu:
+            y = F.silu(y)
+        y = y.permute(0, 2, 3, 1)
+        if addend is not None:
+            y = y + addend
+        return y.contiguous().to(out_dtype)
+
+    def im2col_s2(self, x):
+        Fr, H, W, C = x.shape
+        Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        xp = F.pad(x, (0, 0, 1, 1, 1, 1))
+        cols = torch.stack([xp[:, i:i + 2 * Ho:2, j:j + 2 * Wo:2, :] for i in range(3) for j in range(3)], dim=3)
+        return cols.reshape(Fr * Ho * Wo, 9 * C), (Fr, Ho, Wo)
+
+    def upsample2x(self, x):
+        return x.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
+
+    def concat_add(self, h, skip, ctrl):
+        return torch.cat([h, skip if ctrl is None else skip + ctrl], dim=-1)
+
+    def add_(self, x, y):
+        return x.add_(y)
+
+    def cast_bf16(self, x):
+        return x.to(torch.bfloat16)
+
+    def nchw_to_nhwc(self, x, out=None, ch_off=0):
+        y = x.permute(0, 2, 3, 1)
+        if out is None:
+            return y.contiguous()
+        out[..., ch_off:ch_off + x.shape[1]] = y
+        return out
+
+    def nhwc_to_nchw(self, x):
+        return x.permute(0, 3, 1, 2).contiguous()
+
+    def timestep_embedding(self, t, dim):
+        half = dim // 2
+        freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=F32) / half)
+        args = t[:, None].float() * freqs[None]
+        return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+
+    def linear_small(self, x, w, bias, silu_in=False, silu_out=False):
+        y = F.linear(F.silu(x) if silu_in else x, w.float(), bias)
+        return F.silu(y) if silu_out else y
+
+    def cfg_euler_step(self, x, eps2, x_in_next, sigma, sigma_next, scale, c_in_next):
+        n = x.shape[0]
+        den_u = eps2[:n] * (-sigma) + x
+        den_c = eps2[n:] * (-sigma) + x
+        den = den_u + scale * (den_c - den_u)
+        x.copy_(x + (sigma_next - sigma) * ((x - den) / sigma))
+        if x_in_next is not None:
+            x_in_next.copy_(torch.cat([x, x]) * c_in_next)
+        return x
+
+    def scale_dup(self, x, s, copies):
+        return torch.cat([x * s] * copies)
