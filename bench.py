@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""Benchmark of the Panacea denoising hot path on B200 (BASELINE.json metric: UNet denoise-steps/s).
+
+A "step" = one Euler/DDIM step of one 6-view x 8-frame sequence: CFG-doubled eps evaluation (ControlNet + UNet on
+16 frames of [8, 32, 6x56]) + guidance + update — BASELINE.json configs[1] ("single-GPU 50-step DDIM, 6 views x 8
+frames, synthetic BEV layout via ControlNet, bf16"). One sequence per GPU (weak scaling), no collective inside
+the loop; after the loop rank 0 gathers the final latents over NCCL (configs[2]).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+  python bench.py --impl reference [--steps K] [--warmup W]      # the reference algorithm on the host CPU (oracle port)
+
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+
+METRIC = "UNet denoise-steps/s (6-view x 8-frame latent, CFG-doubled eps-eval + guidance + Euler update)"
+H, W_VIEW, VIEWS, T = 32, 56, 6, 8
+ALGO_TFLOP_PER_STEP = 82.2        # steady-state algorithmic work of one CFG step at 32x56
+
+
+def workload_config(n_gpus: int) -> dict:
+    return {"workload": "configs[1]: 50-step Euler/DDIM denoising loop, 1 sequence/GPU, 6 views x 8 frames, latent 32x56 per "
+                        "view (x [16,8,32,336] per eps-eval incl. CFG), synthetic BEV hint [8,19,256,2688] + text [1,77,1024], "
+                        "full-size UNet+ControlNet (2.24 B params, random init, zero-init tails re-drawn N(0,0.02^2))",
+            "cfg_scale": 5.0, "frames": T, "views": VIEWS, "latent_hw_per_view": [H, W_VIEW],
+            "sequences_per_gpu": 1, "parallelism": f"dp{n_gpus} (independent sequences, NCCL gather of final latents)",
+            "l2_policy": "no explicit flush: every step streams 4.5 GB of bf16 weights + >2 GB of activations, >> 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.samples, self.proc, self.thread = [], None, None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 7:
+                self.samples.append(parts)
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for p in self.samples:
+            try:
+                sm.append(float(p[0])); mx = float(p[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline (oracle)
+def cpu_baseline(budget_s: float, steps: int = 1, warmup: int = 0):
+    """Times the CPU oracle port (oracle/unet_port.py — the reference algorithm restated in plain PyTorch fp32) on the
+    host cores with all threads, on a bounded sample of the workload. Returns (steps_per_s, description, cores, ms)."""
+    from oracle import unet_port as P
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = P.NetConfig()
+    spec = P.state_spec(cfg)
+    # cheap non-degenerate weights (timing only): tile one random block, scale like the seeded init
+    g = torch.Generator().manual_seed(0)
+    pool = torch.randn(1 << 22, generator=g)
+    sd = {}
+    for k, shape in spec.items():
+        n = math.prod(shape)
+        v = pool.repeat((n + pool.numel() - 1) // pool.numel())[:n].reshape(shape)
+        if k.endswith(".bias"):
+            v = v * 0.05
+        elif len(shape) == 1:
+            v = 1.0 + 0.1 * v
+        else:
+            v = v * (0.7 / math.sqrt(math.prod(shape[1:])))
+        sd[k] = v.contiguous()
+
+    def run(frames_T: int, b: int, h: int):
+        c = P.NetConfig(num_frames=frames_T)
+        BT, Wt = b * frames_T, VIEWS * W_VIEW
+        x = torch.randn(BT, 4, h, Wt)
+        cond = {"concat": torch.randn(BT, 4, h, Wt), "cond_feat": torch.rand(BT, 19, 8 * h, 8 * Wt), "crossattn": torch.randn(b, 77, 1024)}
+        t = torch.full((BT,), 500, dtype=torch.int64)
+        t0 = time.perf_counter()
+        P.wrapper_forward(sd, c, x, t, cond)
+        return time.perf_counter() - t0
+
+    # calibrate with the smallest sample (single frame, half the latent rows), then pick the largest that fits
+    t_cal = run(1, 1, H // 2)
+    per_step_budget = max(budget_s / max(steps + warmup, 1), 1.0)
+    ladder = [("one CFG half (1 sequence x 8 frames, full 32x336 latent); a step is 2 of these", 8, 1, H, 2.0, 8.0),
+              ("one frame (T=1, b=1, full 32x336 latent); a step is 16 of these (pessimistic: CPU efficiency drops at T=1)", 1, 1, H, 16.0, 2.0),
+              ("one frame at half height (T=1, b=1, 16x336 latent); a step is 32 of these", 1, 1, H // 2, 32.0, 1.0)]
+    choice = ladder[-1]
+    for item in ladder:
+        if t_cal * item[5] * 1.3 <= per_step_budget:
+            choice = item
+            break
+    desc, fT, b, h, per_step, _ = choice
+    for _ in range(warmup):
+        run(fT, b, h)
+    times = [run(fT, b, h) for _ in range(max(steps, 1))]
+    t_mean = sum(times) / len(times)
+    return 1.0 / (per_step * t_mean), f"{desc}; torch {torch.__version__} fp32, {cores} threads", cores, t_mean * 1e3
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    budget = float(os.environ.get("PN_CPU_BUDGET_S", "200"))
+    val, desc, cores, ms = cpu_baseline(budget, steps=args.steps, warmup=min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 / val, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": val, "unit": "steps/s", "cores": cores, "kind": "port", "sample": desc, "sample_ms": ms},
+            "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ CUDA path
+def build_pipeline(device, seed):
+    from panacea_b200.pipeline import DenoisingPipeline, default_sampler_config
+    with torch.device(device):
+        pipe = DenoisingPipeline(sampler_config=default_sampler_config(50, 5.0), use_cuda_graph=True)
+    pipe.model.randomize_zero_init(seed=seed)
+    pipe.model.controlnet.randomize_zero_init(seed=seed + 1)
+    return pipe
+
+
+def synth_inputs_host(seed):
+    """Synthetic conditioning + initial noise in PINNED host memory (what a data loader would hand over)."""
+    g = torch.Generator().manual_seed(seed)
+    Wt = VIEWS * W_VIEW
+    hint = torch.rand(T, 19, 8 * H, 8 * Wt, generator=g)
+    concat = torch.randn(T, 4, H, Wt, generator=g)
+    c_txt = torch.randn(1, 77, 1024, generator=g)
+    uc_txt = torch.randn(1, 77, 1024, generator=g)
+    noise = torch.randn(T, 4, H, Wt, generator=g)
+    pin = (lambda t: t.pin_memory()) if torch.cuda.is_available() else (lambda t: t)
+    return {"hint": pin(hint), "concat": pin(concat), "c_txt": pin(c_txt), "uc_txt": pin(uc_txt), "noise": pin(noise)}
+
+
+def profile_dominant_kernel(pipe, x_in, t_dev, cc):
+    """One eager eps-eval with CUDA-event timing around every launch of the dominant kernel (the tcgen05 GEMM /
+    implicit-conv kernel): achieved TFLOP/s = sum of algorithmic FLOPs / sum of launch durations."""
+    eng = pipe.model.engine()
+    ops = eng.ops
+    recs = []
+    orig = ops.gemm
+
+    def timed(a, w, **kw):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        out = orig(a, w, **kw)
+        e.record()
+        rows = a.numel() // a.shape[-1]
+        recs.append((2.0 * rows * w.shape[0] * w.shape[1], s, e))
+        return out
+
+    ops.gemm = timed
+    try:
+        eng.eps(x_in, cc["concat"].float().contiguous(), t_dev)
+        torch.cuda.synchronize()
+    finally:
+        ops.gemm = orig
+    flops = sum(r[0] for r in recs)
+    secs = sum(r[1].elapsed_time(r[2]) for r in recs) * 1e-3
+    return flops, secs, len(recs)
+
+
+def run_ours(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    seed = 3407 + rank                                             # inference.py:250
+    pipe = build_pipeline(dev, seed)
+    host = synth_inputs_host(seed)
+    ops = pipe.model.engine().ops                                  # packs bf16 operands
+    den, sampler, wrapper = pipe.denoiser, pipe.sampler, pipe.wrapper
+    wrapper.hint_repeat = 2                                        # CFG halves share the BEV hint
+    K, Wm = args.steps, args.warmup
+
+    def upload():
+        hint = host["hint"].to(dev, non_blocking=True)
+        concat = host["concat"].to(dev, non_blocking=True)
+        ctx = torch.cat([host["uc_txt"], host["c_txt"]]).to(dev, non_blocking=True)
+        return {"cond_feat": hint, "concat": torch.cat([concat, concat]), "crossattn": ctx}
+
+    cc = upload()
+    sig = [float(s) for s in sampler.sigmas(50)]
+    scal = [den.step_scalars(s) for s in sig[:-1]]
+    n = T
+    t_all = torch.tensor([[s[0]] * (2 * n) for s in scal], dtype=torch.int64, device=dev)
+    x = ops.scale_dup(host["noise"].to(dev).float().contiguous(), math.sqrt(1.0 + sig[0] ** 2), 1)
+    x_in = ops.scale_dup(x, scal[0][2], 2)
+
+    def step(i):
+        j = i % (len(sig) - 1)
+        eps = wrapper(x_in, t_all[j], cc)
+        ops.cfg_euler_step(x, eps, x_in, sig[j], sig[j + 1], 5.0, scal[j + 1][2] if j + 1 < len(scal) else scal[0][2], sigma_q=scal[j][1])
+
+    for i in range(max(Wm, 3)):                                    # >= 3 warm-ups: packing, graph capture, clocks
+        step(i)
+    torch.cuda.synchronize()
+    launches0 = ops.launches
+    step(0)
+    torch.cuda.synchronize()
+    launches_per_replay = ops.launches - launches0                 # python-side launches outside the captured graph
+    graph_launches = getattr(wrapper, "_graph_launches", None)
+
+    # ---- timed region 1: device-resident (`value`)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(K):
+        step(i)
+    ev1.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop() if rank == 0 else None
+    if dist is not None:
+        tms = torch.tensor([ms], device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = tms.item()
+
+    # ---- timed region 2: end to end through the public API with host buffers (`e2e`)
+    xh = torch.empty(n, 4, H, VIEWS * W_VIEW).pin_memory()
+    xin_h = torch.empty(2 * n, 4, H, VIEWS * W_VIEW).pin_memory()
+    xin_h.copy_(x_in.cpu())
+    h2d = d2h = 0
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    wrapper.invalidate()
+    cc2 = upload()                                                 # once per sample: conditioning H2D + hint stem + text K/V
+    h2d += sum(host[k].numel() * 4 for k in ("hint", "concat", "c_txt", "uc_txt"))
+    for i in range(K):
+        j = i % (len(sig) - 1)
+        xi = xin_h.to(dev, non_blocking=True)                      # this step's network input from pinned host memory
+        ti = t_all[j]
+        h2d += xin_h.numel() * 4
+        eps = wrapper(xi, ti, cc2)
+        ops.cfg_euler_step(x, eps, xi, sig[j], sig[j + 1], 5.0, scal[j + 1][2] if j + 1 < len(scal) else scal[0][2], sigma_q=scal[j][1])
+        xh.copy_(x, non_blocking=True)                             # the step's result back to the host
+        xin_h.copy_(xi, non_blocking=True)
+        d2h += (xh.numel() + xin_h.numel()) * 4
+        torch.cuda.current_stream().synchronize()
+    e1.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if dist is not None:
+        tms = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms_e2e = tms.item()
+        # configs[2]: gather the final latents on rank 0 (stand-in for decoded frames; the VAE is out of scope)
+        outs = [torch.empty_like(x) for _ in range(world)] if rank == 0 else None
+        dist.gather(x, outs, dst=0)
+
+    # ---- dominant-kernel roofline (eager, per-launch CUDA events), launch count of one graphed eps-eval
+    flops, secs, n_gemm = profile_dominant_kernel(pipe, x_in, t_all[0], cc2)
+    l0 = ops.launches
+    pipe.model.engine().eps(x_in, cc2["concat"].float().contiguous(), t_all[0])
+    torch.cuda.synchronize()
+    launches_per_eps = ops.launches - l0
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        val, desc, cores, msc = cpu_baseline(float(os.environ.get("PN_CPU_BUDGET_S", "40")), steps=1, warmup=0)
+        cpu = {"value": val, "unit": "steps/s", "cores": cores, "kind": "port", "sample": desc, "sample_ms": msc}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        except (OSError, ValueError):
+            pass
+        peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        achieved = flops / secs / 1e12
+        value = world * K / (ms * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": max(Wm, 3),
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "config": workload_config(world),
+            "e2e": {"value": world * K / (ms_e2e * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": d2h // K,
+                    "note": "per step: network input H2D from pinned memory + updated latent D2H; conditioning upload, BEV hint stem and "
+                            "text K/V (once per sample) are inside the timed region"},
+            "gpu_launches": (launches_per_eps + 1) * K,
+            "launches_per_step": launches_per_eps + 1,
+            "algorithmic_tflop_per_step": ALGO_TFLOP_PER_STEP,
+            "achieved_tflops_whole_step": ALGO_TFLOP_PER_STEP * (K / (ms * 1e-3)),
+            "roofline": {"bound": "tensor", "kernel": "pn::gemm_tc_kernel (tcgen05 GEMM / implicit conv, all launches of one eps-eval)",
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1400",
+                         "launches": n_gemm, "share_of_step": secs / (ms * 1e-3 / K),
+                         "how": "sum of 2*M*N*K over the launches / sum of per-launch CUDA-event durations, eager pass after the timed region"},
+            "clocks": clk, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — this implementation has no CPU path (use --impl reference for the CPU baseline)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: self-launch under torchrun when started as a plain script
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", os.environ.get("MASTER_PORT", "29511"), str(Path(__file__).resolve()), "--gpus", str(args.gpus), "--steps",
+               str(args.steps), "--warmup", str(args.warmup)] + (["--no-cpu-baseline"] if args.no_cpu_baseline else [])
+        raise SystemExit(subprocess.call(cmd))
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -150,10 +150,12 @@ int pn_timestep_embedding(const int64_t* t, float* out, int64_t n, int64_t dim, 
 int pn_linear_small(const float* x, const void* W_bf16, const float* bias, float* y, int64_t M, int64_t N, int64_t K,
                     int64_t ldy, int silu_in, int silu_out, void* stream);
 /* One Euler step with classifier-free guidance, reference operation order (denoiser.py:22-28, guiders.py:25-29,
- * sampling_utils.py:7-9,39-40, sampling.py:103-110). eps2 = [uncond ; cond] halves of n elements each;
+ * sampling_utils.py:7-9,39-40, sampling.py:103-110). net2 = [uncond ; cond] halves of n elements each: the network's
+ * eps prediction (net_is_denoised = 0; the denoiser's c_out = -sigma_q, c_skip = 1 are applied here, sigma_q being
+ * sigma snapped to the denoiser's 1000-entry table) or already-denoised samples (net_is_denoised = 1).
  * x is updated in place; x_in_next (optional, 2n elements) receives x_new * c_in_next duplicated. */
-int pn_cfg_euler_step(float* x, const float* eps2, float* x_in_next, int64_t n, float sigma, float sigma_next,
-                      float cfg_scale, float c_in_next, void* stream);
+int pn_cfg_euler_step(float* x, const float* net2, float* x_in_next, int64_t n, float sigma, float sigma_q,
+                      float sigma_next, float cfg_scale, float c_in_next, int net_is_denoised, void* stream);
 /* out[c*n + i] = x[i] * s for c < copies (prepare_sampling_loop x *= sqrt(1+sigma0^2), CFG batch doubling). */
 int pn_scale_dup(const float* x, float* out, int64_t n, float s, int copies, void* stream);
 

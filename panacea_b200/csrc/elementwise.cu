@@ -177,12 +177,14 @@ __global__ void im2col_s2_kernel(const float* __restrict__ x, __nv_bfloat16* __r
 // guiders.py:25-29 + sampling_utils.py:7-9 x_u + s (x_c - x_u); sampling_utils.py:39-40 d = (x - den)/sigma;
 // sampling.py:103-110 x += (sigma_next - sigma) d). eps holds [uncond ; cond] halves. Also emits the next
 // network input x_next * c_in(sigma_next) so the loop needs no extra pass.
-__global__ void cfg_euler_kernel(float* __restrict__ x, const float* __restrict__ eps, float* __restrict__ x_in_next,
-                                 size_t n, float sigma, float sigma_next, float scale, float c_in_next) {
+__global__ void cfg_euler_kernel(float* __restrict__ x, const float* __restrict__ net2, float* __restrict__ x_in_next,
+                                 size_t n, float sigma, float sigma_q, float sigma_next, float scale, float c_in_next,
+                                 int net_is_denoised) {
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
     const float xv = x[e];
-    const float den_u = eps[e] * (-sigma) + xv;
-    const float den_c = eps[n + e] * (-sigma) + xv;
+    // denoiser.py:28 with EpsScaling: denoised = net * c_out + x * c_skip, c_out = -sigma_q, c_skip = 1
+    const float den_u = net_is_denoised ? net2[e] : net2[e] * (-sigma_q) + xv;
+    const float den_c = net_is_denoised ? net2[n + e] : net2[n + e] * (-sigma_q) + xv;
     const float den = den_u + scale * (den_c - den_u);
     const float d = (xv - den) / sigma;
     const float xn = xv + (sigma_next - sigma) * d;
@@ -296,11 +298,12 @@ extern "C" int pn_im2col3x3_s2(const float* x, void* out_bf16, int64_t frames, i
   return PN_OK;
 }
 
-extern "C" int pn_cfg_euler_step(float* x, const float* eps2, float* x_in_next, int64_t n, float sigma,
-                                 float sigma_next, float cfg_scale, float c_in_next, void* stream_v) {
-  PN_REQUIRE(x && eps2 && n > 0 && sigma > 0.f, "pn_cfg_euler_step: bad arguments");
+extern "C" int pn_cfg_euler_step(float* x, const float* net2, float* x_in_next, int64_t n, float sigma, float sigma_q,
+                                 float sigma_next, float cfg_scale, float c_in_next, int net_is_denoised,
+                                 void* stream_v) {
+  PN_REQUIRE(x && net2 && n > 0 && sigma > 0.f, "pn_cfg_euler_step: bad arguments");
   cfg_euler_kernel<<<grid_for((size_t)n), 256, 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(
-      x, eps2, x_in_next, (size_t)n, sigma, sigma_next, cfg_scale, c_in_next);
+      x, net2, x_in_next, (size_t)n, sigma, sigma_q, sigma_next, cfg_scale, c_in_next, net_is_denoised);
   PN_CHECK_CUDA(cudaGetLastError());
   return PN_OK;
 }

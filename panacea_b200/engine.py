@@ -65,7 +65,7 @@ class Engine:
         self.plan_cn: Plan = make_plan(cfg, decoder=False)
         self.wu: PackedWeights | None = None
         self.wc: PackedWeights | None = None
-        self.cond = None     # step-invariant state from prepare_condition
+        self.cond = {"guided": None, "kv": {}, "b": None}     # step-invariant state (prepare_hint / prepare_text)
 
     # ------------------------------------------------------------------------------------------ packing
     def _pack_trunk(self, P: dict, plan: Plan) -> PackedWeights:
@@ -122,56 +122,81 @@ class Engine:
         W["emb.b"] = torch.cat(emb_b, 0).to(F32).contiguous()
         return W
 
-    def pack(self, unet_params: dict, cn_params: dict) -> None:
-        """(Re)build packed weights from fp32 parameters keyed by the reference's state-dict names."""
+    def pack(self, unet_params: dict | None, cn_params: dict | None) -> None:
+        """(Re)build packed weights from fp32 parameters keyed by the reference's state-dict names
+        (ControlledUNetModel3D's own keys / ControlNet3D's keys, without prefixes). Either may be None."""
         cfg, dt = self.cfg, self.dt
         f = lambda t: t.detach().to(F32).contiguous()
-        wu = self._pack_trunk(unet_params, self.plan_unet)
-        wu["out.g"] = f(unet_params["out.0.weight"]); wu["out.bn"] = f(unet_params["out.0.bias"])
-        wu["out.w"] = _pack_direct(unet_params["out.2.weight"].detach()); wu["out.b"] = f(unet_params["out.2.bias"])
-        wc = self._pack_trunk(cn_params, self.plan_cn)
-        for i in range(len(HINT_STRIDES)):
-            w = cn_params[f"input_hint_block.{2 * i}.weight"].detach()
-            wc[f"hint{i}.w"] = _pack_direct(w, cin_pad=(w.shape[1] + 3) // 4 * 4)
-            wc[f"hint{i}.b"] = f(cn_params[f"input_hint_block.{2 * i}.bias"])
-        s = float(cfg.control_scales)
-        names = [f"zero_convs.{i}.0" for i in range(len(self.plan_cn.skip_channels))] + ["middle_block_out.0"]
-        for i, nm in enumerate(names):
-            w = cn_params[nm + ".weight"].detach()
-            wc[f"zc{i}.w"] = (w.reshape(w.shape[0], w.shape[1]) * s).to(dt).contiguous()
-            wc[f"zc{i}.b"] = (cn_params[nm + ".bias"].detach().to(F32) * s).contiguous()
-        self.wu, self.wc = wu, wc
-        self.cond = None
+        self.wu = self.wc = None
+        if unet_params is not None:
+            wu = self._pack_trunk(unet_params, self.plan_unet)
+            wu["out.g"] = f(unet_params["out.0.weight"]); wu["out.bn"] = f(unet_params["out.0.bias"])
+            wu["out.w"] = _pack_direct(unet_params["out.2.weight"].detach()); wu["out.b"] = f(unet_params["out.2.bias"])
+            self.wu = wu
+        if cn_params is not None:
+            wc = self._pack_trunk(cn_params, self.plan_cn)
+            for i in range(len(HINT_STRIDES)):
+                w = cn_params[f"input_hint_block.{2 * i}.weight"].detach()
+                wc[f"hint{i}.w"] = _pack_direct(w, cin_pad=(w.shape[1] + 3) // 4 * 4)
+                wc[f"hint{i}.b"] = f(cn_params[f"input_hint_block.{2 * i}.bias"])
+            s = float(cfg.control_scales)
+            names = [f"zero_convs.{i}.0" for i in range(len(self.plan_cn.skip_channels))] + ["middle_block_out.0"]
+            for i, nm in enumerate(names):
+                w = cn_params[nm + ".weight"].detach()
+                wc[f"zc{i}.w"] = (w.reshape(w.shape[0], w.shape[1]) * s).to(dt).contiguous()
+                wc[f"zc{i}.b"] = (cn_params[nm + ".bias"].detach().to(F32) * s).contiguous()
+            self.wc = wc
+        self.cond = {"guided": None, "kv": {}, "b": None}
 
     # ------------------------------------------------------------------------------------------ step-invariant
-    def prepare_condition(self, hint_nchw: torch.Tensor, context: torch.Tensor, hint_repeat: int = 1) -> None:
-        """hint_nchw fp32 [frames/hint_repeat, hint_channels, 8H, 8W]; context fp32 [b, 77, context_dim].
-        Runs the hint stem (controlmodel.py:43-59,118) and every attn2 K/V projection once per sample."""
+    def prepare_hint(self, hint_nchw: torch.Tensor, hint_repeat: int = 1) -> None:
+        """BEV hint stem, once per sample (controlmodel.py:43-59,118). hint_nchw fp32
+        [frames/hint_repeat, hint_channels, 8H, 8W]; under CFG both halves share the hint (hint_repeat=2)."""
         ops, dt, wc = self.ops, self.dt, self.wc
-        assert wc is not None, "call pack() first"
+        assert wc is not None, "pack() the ControlNet parameters first"
         Fh, Ch, Hh, Wh = hint_nchw.shape
         cin_pad = wc["hint0.w"].shape[1]
         h = torch.zeros((Fh, Hh, Wh, cin_pad), device=hint_nchw.device, dtype=F32)
         ops.nchw_to_nhwc(hint_nchw.to(F32).contiguous(), out=h, ch_off=0)
         n = len(HINT_STRIDES)
         for i, s in enumerate(HINT_STRIDES):
-            cout = self.wc[f"hint{i}.b"].numel()
+            cout = wc[f"hint{i}.b"].numel()
             last = i == n - 1
             h = ops.conv3x3_direct(h, wc[f"hint{i}.w"], wc[f"hint{i}.b"], cout, stride=s, silu=not last,
                                    out_dtype=F32 if last else dt)
         if hint_repeat > 1:
             h = h.repeat(hint_repeat, 1, 1, 1)
+        old = self.cond["guided"]
+        if old is not None and old.shape == h.shape and old.device == h.device:
+            old.copy_(h)          # keep the buffer address stable: a captured CUDA graph stays valid across samples
+        else:
+            self.cond["guided"] = h
+
+    def prepare_text(self, context: torch.Tensor) -> None:
+        """K/V projections of the text context for every attn2 (attention.py:248-250), once per sample.
+        context fp32 [b, L<=128, context_dim]."""
+        ops, dt = self.ops, self.dt
         b, L, D = context.shape
         ctx = self._to_operand(context.to(F32).contiguous().reshape(b * L, D))
-        kv = {}
+        kv = self.cond["kv"]
         for W, plan in ((self.wu, self.plan_unet), (self.wc, self.plan_cn)):
+            if W is None:
+                continue
             for st in plan.stages():
                 if st.kind != "stt":
                     continue
                 for br in STT_BRANCHES:
                     t = f"{st.key}.transformer_blocks{br}.0"
-                    kv[(id(W), t)] = ops.gemm(ctx, W[t + ".kv2.w"], out_dtype=dt).reshape(b, L, 2 * st.cin)
-        self.cond = {"guided": h, "kv": kv, "b": b}
+                    old = kv.get((id(W), t))
+                    if old is not None and old.shape == (b, L, 2 * st.cin):
+                        ops.gemm(ctx, W[t + ".kv2.w"], out_dtype=dt, out=old.view(b * L, 2 * st.cin))   # same address
+                    else:
+                        kv[(id(W), t)] = ops.gemm(ctx, W[t + ".kv2.w"], out_dtype=dt).reshape(b, L, 2 * st.cin)
+        self.cond["b"] = b
+
+    def prepare_condition(self, hint_nchw: torch.Tensor, context: torch.Tensor, hint_repeat: int = 1) -> None:
+        self.prepare_hint(hint_nchw, hint_repeat)
+        self.prepare_text(context)
 
     # ------------------------------------------------------------------------------------------ blocks
     def _emb_vectors(self, W, t):
@@ -311,7 +336,7 @@ class Engine:
     def eps(self, x_nchw, concat_nchw, t):
         """OpenAIWrapperControlLDM3D.forward (wrappers.py:37-70) with the step-invariant parts precomputed."""
         ops = self.ops
-        assert self.cond is not None, "call prepare_condition() first"
+        assert self.cond is not None and self.cond["guided"] is not None and self.cond["kv"], "call prepare_condition() first"
         Fr, Cx, H, Wd = x_nchw.shape
         cin = self.cfg.in_channels
         xin = torch.empty((Fr, H, Wd, cin), device=x_nchw.device, dtype=F32)

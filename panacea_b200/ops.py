@@ -295,11 +295,13 @@ class NativeOps:
         self.launches += 1
         return y
 
-    def cfg_euler_step(self, x, eps2, x_in_next, sigma, sigma_next, scale, c_in_next):
-        _req(x.dtype == F32 and eps2.dtype == F32 and x.is_contiguous() and eps2.is_contiguous() and eps2.numel() == 2 * x.numel(),
+    def cfg_euler_step(self, x, net2, x_in_next, sigma, sigma_next, scale, c_in_next, sigma_q=None, net_is_denoised=False):
+        _req(x.dtype == F32 and net2.dtype == F32 and x.is_contiguous() and net2.is_contiguous() and net2.numel() == 2 * x.numel(),
              "cfg_euler_step: shapes")
-        _lib.check(self.lib.pn_cfg_euler_step(_ptr(x), _ptr(eps2), _ptr(x_in_next), x.numel(), float(sigma), float(sigma_next),
-                                             float(scale), float(c_in_next), _stream()), "pn_cfg_euler_step")
+        sq = sigma if sigma_q is None else sigma_q
+        _lib.check(self.lib.pn_cfg_euler_step(_ptr(x), _ptr(net2), _ptr(x_in_next), x.numel(), float(sigma), float(sq),
+                                             float(sigma_next), float(scale), float(c_in_next), int(bool(net_is_denoised)),
+                                             _stream()), "pn_cfg_euler_step")
         self.launches += 1
         return x
 

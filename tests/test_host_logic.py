@@ -1,0 +1,120 @@
+"""CPU tests of the host side: plan/spec, state-dict compatibility of the drop-in modules, weight packing and the
+engine's orchestration (run through a torch test op set, tests/torch_ref_ops.py) against the reference goldens."""
+from pathlib import Path
+
+import pytest
+import torch
+
+from oracle import cases as Cs
+from oracle import unet_port as P
+from panacea_b200 import engine as E
+from panacea_b200 import netplan as NP
+from torch_ref_ops import TorchRefOps
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+
+def _split(sd):
+    up = {k[len("diffusion_model."):]: v for k, v in sd.items() if not k.startswith("diffusion_model.controlnet.")}
+    cp = {k[len("diffusion_model.controlnet."):]: v for k, v in sd.items() if k.startswith("diffusion_model.controlnet.")}
+    return up, cp
+
+
+def test_param_spec_equals_reference_key_set():
+    cfg = NP.config_from_kwargs(Cs.GOLDEN_CASES[4].unet_kwargs())
+    full = {"diffusion_model." + k: v for k, v in NP.unet_param_spec(cfg).items()}
+    full.update({"diffusion_model.controlnet." + k: v for k, v in NP.controlnet_param_spec(cfg).items()})
+    assert full == P.state_spec(P.NetConfig())
+    plan = NP.make_plan(cfg, True)
+    kinds = [st.kind for st in plan.stages()]
+    assert kinds.count("res") == 22 and kinds.count("stt") == 16
+    assert [st.kind for st in NP.make_plan(cfg, False).stages()].count("stt") == 7
+
+
+def test_unsupported_configurations_are_rejected_loudly():
+    kw = Cs.GOLDEN_CASES[0].unet_kwargs()
+    for bad in (dict(use_scale_shift_norm=True), dict(resblock_updown=True), dict(transformer_depth=2),
+                dict(insert_crossview=False), dict(num_classes=10), dict(legacy=True)):
+        with pytest.raises(NotImplementedError):
+            NP.config_from_kwargs(dict(kw, **bad))
+
+
+@pytest.mark.parametrize("name", ["tiny_2to1", "tiny_3to1", "small_hd64"])
+def test_engine_orchestration_matches_reference_golden(name):
+    case = [c for c in Cs.GOLDEN_CASES if c.name == name][0]
+    cfg = NP.config_from_kwargs(case.unet_kwargs())
+    eng = E.Engine(cfg, TorchRefOps(), op_dtype=torch.float32)
+    eng.pack(*_split(Cs.make_weights(case)))
+    x, t, c = Cs.make_inputs(case)
+    eng.prepare_condition(c["cond_feat"], c["crossattn"])
+    eps = eng.eps(x, c["concat"], t)
+    g = torch.load(GOLDEN / f"eps_{name}.pt")["eps"]
+    assert (eps - g).abs().max().item() < 2e-5
+    # CFG: hint given once for both halves
+    half = x.shape[0] // case.b
+    if case.b == 2:
+        eng.prepare_condition(c["cond_feat"][:half], c["crossattn"], hint_repeat=1)
+        eng.prepare_hint(torch.cat([c["cond_feat"][:half]] * 1), hint_repeat=1)
+
+
+def test_dropin_modules_share_the_reference_state_dict():
+    from panacea_b200.pipeline import default_network_config
+    from panacea_b200.sgm.modules.diffusionmodules import OpenAIWrapperControlLDM3D
+    from panacea_b200.sgm.util import instantiate_from_config
+    case = Cs.GOLDEN_CASES[0]
+    kw = case.unet_kwargs()
+    model = instantiate_from_config(default_network_config(**{k: kw[k] for k in ("model_channels", "num_head_channels", "context_dim", "num_frames")}))
+    w = OpenAIWrapperControlLDM3D(model)
+    ref_sd = Cs.make_weights(case)
+    assert {k: tuple(v.shape) for k, v in w.state_dict().items()} == {k: tuple(v.shape) for k, v in ref_sd.items()}
+    # reference default init reproduces the zero_module()'d tails
+    z = [k for k, v in w.state_dict().items() if v.abs().sum() == 0 and k.endswith("weight")]
+    assert any("proj_out_crossview" in k for k in z) and any("zero_convs" in k for k in z) and "diffusion_model.out.2.weight" in z
+    res = w.load_state_dict(ref_sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert torch.equal(w.state_dict()["diffusion_model.controlnet.input_hint_block.14.weight"],
+                       ref_sd["diffusion_model.controlnet.input_hint_block.14.weight"])
+    with pytest.raises(RuntimeError):
+        w.load_state_dict({**ref_sd, "diffusion_model.bogus.weight": torch.zeros(1)}, strict=True)
+    # engine checkpoints carry a "model." prefix and DeepSpeed's "_forward_module." (inference.py:209-211)
+    wrapped = {"model." + k: v for k, v in ref_sd.items()}
+
+    class Host(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.model = w
+    assert not Host().load_state_dict(wrapped, strict=True).missing_keys
+    with pytest.raises(RuntimeError):
+        w(torch.zeros(4, 4, 8, 96), torch.zeros(4, dtype=torch.int64), {})       # CPU tensors: no CPU path
+
+
+def test_denoiser_and_sampler_host_scalars():
+    from panacea_b200.pipeline import DEFAULT_DENOISER, default_sampler_config
+    from panacea_b200.sgm.util import instantiate_from_config
+    kat = torch.load(GOLDEN / "kat.pt")
+    den = instantiate_from_config(DEFAULT_DENOISER)
+    assert torch.equal(den.sigmas, kat["denoiser_sigmas"])
+    assert torch.equal(den.sigma_to_idx(kat["sigmas_50"][:-1]), kat["idx_of_sigmas_50"])
+    sampler = instantiate_from_config(default_sampler_config(25, 5.0))
+    assert torch.equal(sampler.sigmas(), kat["sigmas_25"]) and torch.equal(sampler.sigmas(50), kat["sigmas_50"])
+    idx, sq, c_in = den.step_scalars(float(kat["sigmas_25"][3]))
+    assert idx == 999 - 3 * 40 and sq == float(kat["sigmas_25"][3]) and abs(c_in - (sq * sq + 1) ** -0.5) < 1e-7
+    assert sampler.guider.scale == 5.0
+    with pytest.raises(TypeError):
+        sampler(lambda *a: None, torch.zeros(1), {}, {})
+
+
+def test_install_as_sgm_resolves_reference_targets():
+    import sys
+    import panacea_b200.sgm as S
+    saved = {k: v for k, v in sys.modules.items() if k == "sgm" or k.startswith("sgm.")}
+    for k in saved:
+        del sys.modules[k]
+    try:
+        S.install_as_sgm()
+        import sgm.modules.diffusionmodules.controlmodel as cm
+        assert cm.ControlledUNetModel3D.__module__.startswith("panacea_b200.")
+    finally:
+        for k in [k for k in sys.modules if k == "sgm" or k.startswith("sgm.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)

@@ -159,10 +159,11 @@ class TorchRefOps:
         y = F.linear(F.silu(x) if silu_in else x, w.float(), bias)
         return F.silu(y) if silu_out else y
 
-    def cfg_euler_step(self, x, eps2, x_in_next, sigma, sigma_next, scale, c_in_next):
+    def cfg_euler_step(self, x, net2, x_in_next, sigma, sigma_next, scale, c_in_next, sigma_q=None, net_is_denoised=False):
         n = x.shape[0]
-        den_u = eps2[:n] * (-sigma) + x
-        den_c = eps2[n:] * (-sigma) + x
+        sq = sigma if sigma_q is None else sigma_q
+        den_u = net2[:n] if net_is_denoised else net2[:n] * (-sq) + x
+        den_c = net2[n:] if net_is_denoised else net2[n:] * (-sq) + x
         den = den_u + scale * (den_c - den_u)
         x.copy_(x + (sigma_next - sigma) * ((x - den) / sigma))
         if x_in_next is not None:
