@@ -34,6 +34,14 @@ H, W_VIEW, VIEWS, T = 32, 56, 6, 8
 ALGO_TFLOP_PER_STEP = 82.2        # steady-state algorithmic work of one CFG step at 32x56
 
 
+_T0 = time.time()
+
+
+def log(msg: str) -> None:
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(f"[bench +{time.time() - _T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def workload_config(n_gpus: int) -> dict:
     return {"workload": "configs[1]: 50-step Euler/DDIM denoising loop, 1 sequence/GPU, 6 views x 8 frames, latent 32x56 per "
                         "view (x [16,8,32,336] per eps-eval incl. CFG), synthetic BEV hint [8,19,256,2688] + text [1,77,1024], "
@@ -216,9 +224,12 @@ def run_ours(args) -> None:
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     seed = 3407 + rank                                             # inference.py:250
+    log("building full-size UNet + ControlNet on the device")
     pipe = build_pipeline(dev, seed)
+    log("synthetic host inputs (pinned)")
     host = synth_inputs_host(seed)
     ops = pipe.model.engine().ops                                  # packs bf16 operands
+    log("weights packed")
     den, sampler, wrapper = pipe.denoiser, pipe.sampler, pipe.wrapper
     wrapper.hint_repeat = 2                                        # CFG halves share the BEV hint
     K, Wm = args.steps, args.warmup
@@ -244,7 +255,8 @@ def run_ours(args) -> None:
 
     for i in range(max(Wm, 3)):                                    # >= 3 warm-ups: packing, graph capture, clocks
         step(i)
-    torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        log(f"warm-up step {i} done")
     launches0 = ops.launches
     step(0)
     torch.cuda.synchronize()
@@ -267,6 +279,7 @@ def run_ours(args) -> None:
     if dist is not None:
         dist.barrier()
     ms = ev0.elapsed_time(ev1)
+    log(f"timed region: {K} steps in {ms:.1f} ms")
     clk = clocks.stop() if rank == 0 else None
     if dist is not None:
         tms = torch.tensor([ms], device=dev)
@@ -302,6 +315,7 @@ def run_ours(args) -> None:
     if dist is not None:
         dist.barrier()
     ms_e2e = e0.elapsed_time(e1)
+    log(f"e2e region: {K} steps in {ms_e2e:.1f} ms")
     if dist is not None:
         tms = torch.tensor([ms_e2e], device=dev)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -316,10 +330,13 @@ def run_ours(args) -> None:
     pipe.model.engine().eps(x_in, cc2["concat"].float().contiguous(), t_all[0])
     torch.cuda.synchronize()
     launches_per_eps = ops.launches - l0
+    log(f"profiled dominant kernel: {n_gemm} launches, {flops / secs / 1e12:.0f} TF/s; {launches_per_eps} launches per eps-eval")
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        log("CPU baseline (oracle port) ...")
         val, desc, cores, msc = cpu_baseline(float(os.environ.get("PN_CPU_BUDGET_S", "40")), steps=1, warmup=0)
+        log(f"CPU baseline: {val:.5f} steps/s on {cores} cores")
         cpu = {"value": val, "unit": "steps/s", "cores": cores, "kind": "port", "sample": desc, "sample_ms": msc}
 
     if rank == 0:

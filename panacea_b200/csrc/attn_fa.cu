@@ -13,10 +13,10 @@
 //   warp 0: TMA producer (Q once; K and V boxes through a 3-stage ring)
 //   warp 1: UMMA issuer   S = Q K^T  (M=128, N=kv_n, K=64)  -> TMEM, double buffered
 //                         PV = P V   (M=128, N=64,  K=kv_n) -> TMEM, double buffered (V is the MN-major B operand)
-//   warps 2-5: softmax, one thread per query row (TMEM lane == row, so max/sum need no shuffles):
-//              tcgen05.ld S -> running max -> exp2 -> bf16 P into 128B-swizzled smem (A operand of PV);
-//              O accumulates in registers with the usual rescale; the PV of block j-1 is folded in while the
-//              tensor core works on block j.
+//   warps 2-9: softmax, two threads per query row (TMEM lane == row; the pair splits the S columns and the
+//              output channels): tcgen05.ld S once -> running max (pair exchange through smem) -> exp2 -> bf16 P
+//              into 128B-swizzled smem (A operand of PV); O accumulates in registers with the usual rescale; the
+//              PV of block j-1 is folded in while the tensor core works on block j.
 #include "common.cuh"
 #include "ptx.cuh"
 #include "../../include/panacea_b200.h"
@@ -25,14 +25,15 @@ namespace pn {
 
 constexpr int FA_D = 64;
 constexpr int FA_STAGES = 3;
-constexpr int FA_THREADS = 192;
+constexpr int FA_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 softmax
 constexpr int FA_TILE_BYTES = 128 * 128;          // 128 rows x 64 bf16
 constexpr int FA_SMEM_Q = 0;
 constexpr int FA_SMEM_K = FA_TILE_BYTES;
 constexpr int FA_SMEM_V = FA_SMEM_K + FA_STAGES * FA_TILE_BYTES;
 constexpr int FA_SMEM_P = FA_SMEM_V + FA_STAGES * FA_TILE_BYTES;   // 2 buffers x 2 atoms x 16 KB
 constexpr int FA_SMEM_BAR = FA_SMEM_P + 4 * FA_TILE_BYTES;
-constexpr int FA_SMEM_TOTAL = FA_SMEM_BAR + 256 + 1024;
+constexpr int FA_SMEM_XCH = FA_SMEM_BAR + 256;                      // row-max / row-sum exchange: [2][2][128] floats
+constexpr int FA_SMEM_TOTAL = FA_SMEM_XCH + 2 * 2 * 128 * 4 + 1024;
 
 struct FaParams {
   CUtensorMap mapQ;
@@ -96,10 +97,10 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
     for (int i = 0; i < FA_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&kv_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 128);
-      mbar_init(&p_full[i], 128);
+      mbar_init(&s_empty[i], 256);
+      mbar_init(&p_full[i], 256);
       mbar_init(&pv_full[i], 1);
-      mbar_init(&pv_empty[i], 128);
+      mbar_init(&pv_empty[i], 256);
     }
     fence_barrier_init();
   }
@@ -179,29 +180,36 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
     }
     issue_pv(nblk - 1);
   } else {
-    // ===================== softmax / output warps: thread == query row =====================
+    // ===================== softmax / output warps =====================
+    // Two threads per query row: warps w and w+4 share a TMEM lane quarter; the first takes the even 16-column
+    // chunks of S and output channels [0,32), the second the odd chunks and channels [32,64). Each reads its S
+    // values from TMEM once (registers), the pair agrees on the running row maximum through shared memory (one
+    // 64-thread named barrier per block), row sums are combined once at the end.
+    const int sw_id = warp - 2;
     const int lane_grp = warp & 3;
+    const int half = sw_id >> 2;
     const int row = lane_grp * 32 + lane;
     const uint32_t lane_addr = uint32_t(lane_grp * 32) << 16;
+    float* xch = reinterpret_cast<float*>(smem + FA_SMEM_XCH);      // [buf][half][row]
     float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
-    float O[FA_D];
+    float O[32];
 #pragma unroll
-    for (int i = 0; i < FA_D; ++i) O[i] = 0.f;
+    for (int i = 0; i < 32; ++i) O[i] = 0.f;
     const int nchunk = p.kv_n / 16;
     const float c = p.scale_log2;
+    const uint32_t bar_id = 1 + lane_grp;
+
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory"); };
 
     auto consume_pv = [&](int i, float alpha) {
       const int buf = i & 1;
       mbar_wait(&pv_full[buf], (uint32_t)((i >> 1) & 1));
       tc_fence_after();
+      uint32_t v[32];
+      tmem_ld_32x32(tm_PV + lane_addr + buf * FA_D + half * 32, v);
+      tmem_ld_wait();
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t v[32];
-        tmem_ld_32x32(tm_PV + lane_addr + buf * FA_D + h * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int t = 0; t < 32; ++t) O[h * 32 + t] = O[h * 32 + t] * alpha + __uint_as_float(v[t]);
-      }
+      for (int t = 0; t < 32; ++t) O[t] = O[t] * alpha + __uint_as_float(v[t]);
       tc_fence_before();
       mbar_arrive(&pv_empty[buf]);
     };
@@ -211,42 +219,54 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
       mbar_wait(&s_full[buf], (uint32_t)((j >> 1) & 1));
       tc_fence_after();
       const uint32_t tS = tm_S + lane_addr + buf * 128;
-      // pass 1: row maximum (columns >= kv_rows are padding)
-      float mx = -INFINITY;
-      for (int ch = 0; ch < nchunk; ++ch) {
-        uint32_t v[16];
-        tmem_ld_32x16(tS + ch * 16, v);
-        tmem_ld_wait();
+      // my chunks of S -> registers (single TMEM pass)
+      uint32_t sv[4][16];
 #pragma unroll
-        for (int t = 0; t < 16; ++t)
-          if (ch * 16 + t < p.kv_rows) mx = fmaxf(mx, __uint_as_float(v[t]));
+      for (int q = 0; q < 4; ++q) {
+        const int ch = half + 2 * q;
+        if (ch < nchunk) tmem_ld_32x16(tS + ch * 16, sv[q]);
       }
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&s_empty[buf]);                 // S buffer may be overwritten by the MMA of block j+2
+      float mx = -INFINITY;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int ch = half + 2 * q;
+        if (ch < nchunk) {
+#pragma unroll
+          for (int t = 0; t < 16; ++t)
+            if (ch * 16 + t < p.kv_rows) mx = fmaxf(mx, __uint_as_float(sv[q][t]));
+        }
+      }
+      float* xb = xch + buf * 256;
+      xb[half * 128 + row] = mx;
+      pair_sync();
+      mx = fmaxf(mx, xb[(half ^ 1) * 128 + row]);
       const float m_new = fmaxf(m_run, mx * c);
       const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_new);
-      // pass 2: p = exp2(s*c - m_new), row sum, bf16 P into the swizzled A-operand buffer
       float rs = 0.f;
       uint8_t* sP = smem + FA_SMEM_P + buf * 2 * FA_TILE_BYTES;
-      for (int ch = 0; ch < nchunk; ++ch) {
-        uint32_t v[16];
-        tmem_ld_32x16(tS + ch * 16, v);
-        tmem_ld_wait();
-        float e[16];
 #pragma unroll
-        for (int t = 0; t < 16; ++t) {
-          const float pv = exp2f(__uint_as_float(v[t]) * c - m_new);
-          e[t] = (ch * 16 + t < p.kv_rows) ? pv : 0.f;
-          rs += e[t];
+      for (int q = 0; q < 4; ++q) {
+        const int ch = half + 2 * q;
+        if (ch < nchunk) {
+          float e[16];
+#pragma unroll
+          for (int t = 0; t < 16; ++t) {
+            const float pv = exp2f(__uint_as_float(sv[q][t]) * c - m_new);
+            e[t] = (ch * 16 + t < p.kv_rows) ? pv : 0.f;
+            rs += e[t];
+          }
+          // 16 keys = 2 chunks of 16 B inside atom (ch/4); chunk index within the 128 B row = (ch%4)*2 + {0,1}
+          uint8_t* atom = sP + (ch >> 2) * FA_TILE_BYTES + row * 128;
+          const int c0 = (ch & 3) * 2;
+          *reinterpret_cast<uint4*>(atom + ((c0 ^ (row & 7)) << 4)) =
+              make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
+          *reinterpret_cast<uint4*>(atom + (((c0 + 1) ^ (row & 7)) << 4)) =
+              make_uint4(pack_bf16x2(e[8], e[9]), pack_bf16x2(e[10], e[11]), pack_bf16x2(e[12], e[13]), pack_bf16x2(e[14], e[15]));
         }
-        // 16 keys = 2 chunks of 16 B inside atom (ch/4); chunk index within the 128 B row = (ch%4)*2 + {0,1}
-        uint8_t* atom = sP + (ch >> 2) * FA_TILE_BYTES + row * 128;
-        const int c0 = (ch & 3) * 2;
-        *reinterpret_cast<uint4*>(atom + ((c0 ^ (row & 7)) << 4)) =
-            make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
-        *reinterpret_cast<uint4*>(atom + (((c0 + 1) ^ (row & 7)) << 4)) =
-            make_uint4(pack_bf16x2(e[8], e[9]), pack_bf16x2(e[10], e[11]), pack_bf16x2(e[12], e[13]), pack_bf16x2(e[14], e[15]));
       }
-      tc_fence_before();
-      mbar_arrive(&s_empty[buf]);
       fence_proxy_async_smem();
       mbar_arrive(&p_full[buf]);
       l_run = l_run * alpha + rs;
@@ -256,15 +276,20 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
     }
     consume_pv(nblk - 1, alpha_prev);
 
-    // normalise and store this row
+    // combine the two partial row sums, normalise and store this thread's 32 channels of the row
+    float* xb = xch + (nblk & 1) * 256;
+    pair_sync();                                  // everyone is past the last max exchange before reuse
+    xb[half * 128 + row] = l_run;
+    pair_sync();
+    const float l_tot = l_run + xb[(half ^ 1) * 128 + row];
     const int yy = row / p.qw, xx = row - yy * p.qw;
     const int x = x0 + xx, y = y0 + yy;
     if (row < p.qw * p.qh && x < p.W && y < p.H) {
-      const float inv = 1.f / l_run;
+      const float inv = 1.f / l_tot;
       const long long token = (((long long)frame * p.H + y) * p.V + view) * p.W + x;
-      __nv_bfloat16* dst = p.out + token * p.out_ld + p.out_ch0 + head * FA_D;
+      __nv_bfloat16* dst = p.out + token * p.out_ld + p.out_ch0 + head * FA_D + half * 32;
 #pragma unroll
-      for (int i = 0; i < FA_D / 8; ++i) {
+      for (int i = 0; i < 4; ++i) {
         *reinterpret_cast<uint4*>(dst + i * 8) =
             make_uint4(pack_bf16x2(O[i * 8 + 0] * inv, O[i * 8 + 1] * inv), pack_bf16x2(O[i * 8 + 2] * inv, O[i * 8 + 3] * inv),
                        pack_bf16x2(O[i * 8 + 4] * inv, O[i * 8 + 5] * inv), pack_bf16x2(O[i * 8 + 6] * inv, O[i * 8 + 7] * inv));

@@ -9,22 +9,23 @@
 // 455-462 Conv2d(padding=1) on the width-concatenated 6-view image; :418,468-476 Conv1d(k=3,padding=1)).
 // B is the packed weight matrix [N, taps*C] (K-major, bf16). Accumulation is fp32 in TMEM.
 //
-// Kernel structure (persistent, one CTA per SM, 192 threads):
+// Kernel structure (persistent, one CTA per SM, 320 threads):
 //   warp 0     : TMA producer  (A box [tn,th,tw,64] + B box [BN,64] per k-block, 128B swizzle)
 //   warp 1     : TMEM alloc + UMMA issuer (tcgen05.mma cta_group::1 kind::f16, M=128, N=BN, K=16)
-//   warps 2..5 : epilogue (tcgen05.ld -> bias/row-vector/GEGLU -> smem transpose -> +residual -> global)
+//   warps 2..9 : epilogue (residual prefetch; tcgen05.ld -> bias/row-vector/GEGLU -> smem transpose -> +residual -> global)
 // Pipelines: smem full/empty ring (TMA<->MMA) and a 2-deep TMEM accumulator ring (MMA<->epilogue) so the
 // epilogue of tile i overlaps the main loop of tile i+1.
 #include "common.cuh"
 #include "ptx.cuh"
 #include "../../include/panacea_b200.h"
 
+#include <cstdlib>
 
 namespace pn {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle atom row
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
 struct GemmParams {
   CUtensorMap mapA;
@@ -48,20 +49,20 @@ struct GemmParams {
   int geglu;
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int NCTA>
 struct GemmSmem {
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (BN / NCTA) * BK * 2;   // a CTA pair splits the N tile: each CTA stages BN/2 weight rows
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGING_BYTES = 4 * 4096;  // per epilogue warp: 32 rows x 128 B
-  static constexpr int ROWMAP_BYTES = 128 * 4;
+  static constexpr int STAGING_BYTES = 8 * 4096;  // per epilogue warp: 32 rows x 128 B
+  static constexpr int ROWMAP_BYTES = 8 * 32 * 4;  // per epilogue warp
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + STAGING_BYTES + ROWMAP_BYTES + BAR_BYTES + 1024;
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int NCTA>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
-  using S = GemmSmem<BN, STAGES>;
+  using S = GemmSmem<BN, STAGES, NCTA>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
@@ -75,10 +76,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // NCTA == 2: the two CTAs of a cluster form a UMMA pair (cta_group::2). Each CTA owns 128 rows of a 256-row
+  // tile (its own A stage and TMEM lanes) and stages half of the N tile's weight rows; the leader (rank 0)
+  // issues the MMAs for both, and the weights cross the L2->SM fabric once per pair instead of once per CTA.
+  const uint32_t cta_rank = (NCTA == 2) ? cluster_ctarank() : 0u;
+  const int unit = (NCTA == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;          // persistent scheduling unit
+  const int num_units = (NCTA == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   const int num_k_blocks = p.taps_h * p.taps_w * p.kc_per_tap;
   const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
-  const int num_tiles = tiles_m * p.tiles_col;
+  const int tiles_m_units = (tiles_m + NCTA - 1) / NCTA;
+  const int num_tiles = tiles_m_units * p.tiles_col;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static_assert(2 * BN <= 512, "two accumulator stages must fit TMEM");
 
@@ -91,29 +99,31 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], 8 * NCTA);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+    if (NCTA == 2) tmem_alloc_2sm(tmem_ptr_smem, TMEM_COLS);
+    else tmem_alloc(tmem_ptr_smem, TMEM_COLS);
   }
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (every CTA loads its own A rows and its share of B) =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = unit; tile < num_tiles; tile += num_units) {
         const int tcol = tile % p.tiles_col;
-        int tm = tile / p.tiles_col;
+        int tm = (tile / p.tiles_col) * NCTA + (int)cta_rank;
         const int twi = tm % p.tiles_w; tm /= p.tiles_w;
         const int thi = tm % p.tiles_h; tm /= p.tiles_h;
-        const int tni = tm;
+        const int tni = tm;                       // >= tiles_n for the odd tail of a pair: fully OOB -> zero fill
         const int x0 = twi * p.tw, y0 = thi * p.th, n0 = tni * p.tn;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           const int tap = kb / p.kc_per_tap;
@@ -123,54 +133,83 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = stage_base + stage * S::STAGE_BYTES;
           uint8_t* sB = sA + S::A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
-          tma_load_4d(sA, &p.mapA, &full_bar[stage], kc * BK, x0 + dx, y0 + dy, n0);
-          tma_load_2d(sB, &p.mapB, &full_bar[stage], kb * BK, tcol * BN);
+          if (NCTA == 2) {
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);   // bytes of both CTAs
+            tma_load_4d_2sm(sA, &p.mapA, &full_bar[stage], kc * BK, x0 + dx, y0 + dy, n0);
+            tma_load_2d_2sm(sB, &p.mapB, &full_bar[stage], kb * BK, tcol * BN + (int)cta_rank * (BN / 2));
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+            tma_load_4d(sA, &p.mapA, &full_bar[stage], kc * BK, x0 + dx, y0 + dy, n0);
+            tma_load_2d(sB, &p.mapB, &full_bar[stage], kb * BK, tcol * BN);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== UMMA issuer =====================
-    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int kb = 0; kb < num_k_blocks; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+    // ===================== UMMA issuer (leader CTA of a pair only) =====================
+    if (cta_rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM * NCTA, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = unit; tile < num_tiles; tile += num_units) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sA = smem_u32(stage_base + stage * S::STAGE_BYTES);
-          const uint32_t sB = sA + S::A_BYTES;
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sA = smem_u32(stage_base + stage * S::STAGE_BYTES);
+            const uint32_t sB = sA + S::A_BYTES;
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = umma_smem_desc(sA + k * 32, 16, 1024);
-            const uint64_t db = umma_smem_desc(sB + k * 32, 16, 1024);
-            umma_f16_ss(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t da = umma_smem_desc(sA + k * 32, 16, 1024);
+              const uint64_t db = umma_smem_desc(sB + k * 32, 16, 1024);
+              if (NCTA == 2) umma_f16_ss_2sm(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              else umma_f16_ss(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            // commit: frees the smem slot (in both CTAs) once the MMAs retire; the last one also publishes the tile
+            if (NCTA == 2) {
+              umma_commit_2sm(&empty_bar[stage], 3);
+              if (kb == num_k_blocks - 1) umma_commit_2sm(&tmem_full[acc], 3);
+            } else {
+              umma_commit(&empty_bar[stage]);
+              if (kb == num_k_blocks - 1) umma_commit(&tmem_full[acc]);
+            }
           }
-          umma_commit(&empty_bar[stage]);                       // frees the smem slot when the MMAs retire
-          if (kb == num_k_blocks - 1) umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
-    // ===================== epilogue warps =====================
-    const int ew = warp - 2;               // staging buffer index
-    const int lane_grp = warp & 3;         // TMEM lane quarter this warp may access
+    // ===================== epilogue warps (8): TMEM lane quarter = warp & 3, chunk parity = (warp - 2) / 4 ==========
+    // Two warps share a lane quarter and split the 32-column chunks between them (even / odd). Everything a warp
+    // needs from global memory for its chunks (the fp32 residual) is requested at tile start, before the accumulator
+    // is even ready, so the DRAM round trip overlaps the main loop instead of serialising the epilogue.
+    const int ew = warp - 2;
+    const int lane_grp = warp & 3;
+    const int half = ew >> 2;
     uint8_t* my_stage = staging + ew * 4096;
+    int* my_rowmap = rowmap + ew * 32;
+    constexpr int NCH = BN / 32;
+    constexpr int MYCH = (NCH + 1) / 2;
+    constexpr int PRECH = MYCH < 3 ? MYCH : 3;   // chunks whose residual is prefetched at tile start (register budget)
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    // hand-back target: the leader CTA's tmem_empty barrier (remote arrive from the peer CTA of a pair)
+    const uint32_t te_addr0 = (NCTA == 2) ? mapa_shared(smem_u32(&tmem_empty[0]), 0) : smem_u32(&tmem_empty[0]);
+    auto release_acc = [&](int a) {
+      if (NCTA == 2) mbar_arrive_cluster(te_addr0 + a * 8);
+      else mbar_arrive(&tmem_empty[a]);
+    };
+    for (int tile = unit; tile < num_tiles; tile += num_units) {
       const int tcol = tile % p.tiles_col;
-      int tm = tile / p.tiles_col;
+      int tm = (tile / p.tiles_col) * NCTA + (int)cta_rank;
       const int twi = tm % p.tiles_w; tm /= p.tiles_w;
       const int thi = tm % p.tiles_h; tm /= p.tiles_h;
       const int tni = tm;
@@ -182,126 +221,168 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         const int dn = r / (p.tw * p.th);
         const int x = twi * p.tw + dx, y = thi * p.th + dy, n = tni * p.tn + dn;
         const bool ok = (x < p.W) && (y < p.H) && (n < p.NB);
-        rowmap[r] = ok ? ((n * p.H + y) * p.W + x) : -1;
+        my_rowmap[lane] = ok ? ((n * p.H + y) * p.W + x) : -1;
       }
       __syncwarp();
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + (uint32_t(lane_grp * 32) << 16) + acc * BN;
-      const int my_row = rowmap[lane_grp * 32 + lane];
+      const int my_row = my_rowmap[lane];
       const int n_base = tcol * BN;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_row + c * 32, v);
-        tmem_ld_wait();
-        if (c == BN / 32 - 1) {
-          // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-        }
-        const int n0 = n_base + c * 32;
-        float f[32];
+      // ---- residual prefetch (fp32 output path): lane -> (row i*4 + lane/8, 16-byte column chunk lane%8)
+      float4 rpre[PRECH][8];
+      const bool pre = (p.residual != nullptr) && !p.out_bf16;
+      if (pre) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (n0 + j < p.N) f[j] += __ldg(p.bias + n0 + j);
-        }
-        if (p.rowvec != nullptr && my_row >= 0) {
-          const float* rv = p.rowvec + (long long)((my_row / p.rows_per_group) % p.n_groups) * p.ldv;
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (n0 + j < p.N) f[j] += __ldg(rv + n0 + j);
-        }
-        if (p.geglu) {
-          // packed weight rows are interleaved (value, gate) pairs: out[n/2] = value * gelu(gate)
-          // (reference GEGLU: attention.py:97-99, chunk order value-first, exact erf GELU)
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = f[2 * j] * gelu_erf(f[2 * j + 1]);
-          // 16 bf16 = 32 B per row
-          uint4* dst = reinterpret_cast<uint4*>(my_stage + lane * 32);
-          dst[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-          dst[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
-          __syncwarp();
-          __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
-          const int no0 = n0 / 2;
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const int rr = i * 16 + (lane >> 1);
-            const int ch = lane & 1;
-            const int grow = rowmap[lane_grp * 32 + rr];
-            if (grow >= 0 && no0 + ch * 8 < p.N / 2) {
-              const uint4 val = *reinterpret_cast<const uint4*>(my_stage + rr * 32 + ch * 16);
-              *reinterpret_cast<uint4*>(out + (long long)grow * p.ldo + no0 + ch * 8) = val;
-            }
-          }
-          __syncwarp();
-        } else if (p.out_bf16) {
-          // 32 bf16 = 64 B per row, 16 B chunks XOR-swizzled with (row>>1)&3
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            const int sw = ch ^ ((lane >> 1) & 3);
-            *reinterpret_cast<uint4*>(my_stage + lane * 64 + sw * 16) =
-                make_uint4(pack_bf16x2(f[ch * 8 + 0], f[ch * 8 + 1]), pack_bf16x2(f[ch * 8 + 2], f[ch * 8 + 3]),
-                           pack_bf16x2(f[ch * 8 + 4], f[ch * 8 + 5]), pack_bf16x2(f[ch * 8 + 6], f[ch * 8 + 7]));
-          }
-          __syncwarp();
-          __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int rr = i * 8 + (lane >> 2);
-            const int ch = lane & 3;
-            const int grow = rowmap[lane_grp * 32 + rr];
-            if (grow >= 0 && n0 + ch * 8 < p.N) {
-              const int sw = ch ^ ((rr >> 1) & 3);
-              uint4 val = *reinterpret_cast<const uint4*>(my_stage + rr * 64 + sw * 16);
-              if (p.residual != nullptr) {
-                const float* rp = p.residual + (long long)grow * p.ldr + n0 + ch * 8;
-                const float4 r0 = *reinterpret_cast<const float4*>(rp);
-                const float4 r1 = *reinterpret_cast<const float4*>(rp + 4);
-                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&val);
-                float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
-                float2 c2 = __bfloat1622float2(h[2]), d = __bfloat1622float2(h[3]);
-                val = make_uint4(pack_bf16x2(a.x + r0.x, a.y + r0.y), pack_bf16x2(b.x + r0.z, b.y + r0.w),
-                                 pack_bf16x2(c2.x + r1.x, c2.y + r1.y), pack_bf16x2(d.x + r1.z, d.y + r1.w));
-              }
-              *reinterpret_cast<uint4*>(out + (long long)grow * p.ldo + n0 + ch * 8) = val;
-            }
-          }
-          __syncwarp();
-        } else {
-          // 32 fp32 = 128 B per row, 16 B chunks XOR-swizzled with row&7 (conflict-free both ways)
-#pragma unroll
-          for (int ch = 0; ch < 8; ++ch) {
-            const int sw = ch ^ (lane & 7);
-            *reinterpret_cast<float4*>(my_stage + lane * 128 + sw * 16) =
-                make_float4(f[ch * 4 + 0], f[ch * 4 + 1], f[ch * 4 + 2], f[ch * 4 + 3]);
-          }
-          __syncwarp();
-          float* out = reinterpret_cast<float*>(p.out);
+        for (int k = 0; k < PRECH; ++k) {
+          const int c = half + 2 * k;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int rr = i * 4 + (lane >> 3);
-            const int ch = lane & 7;
-            const int grow = rowmap[lane_grp * 32 + rr];
-            if (grow >= 0 && n0 + ch * 4 < p.N) {
-              const int sw = ch ^ (rr & 7);
-              float4 val = *reinterpret_cast<const float4*>(my_stage + rr * 128 + sw * 16);
-              if (p.residual != nullptr) {
-                const float4 r = *reinterpret_cast<const float4*>(p.residual + (long long)grow * p.ldr + n0 + ch * 4);
-                val.x += r.x; val.y += r.y; val.z += r.z; val.w += r.w;
+            const int grow = my_rowmap[i * 4 + (lane >> 3)];
+            const int col = n_base + c * 32 + (lane & 7) * 4;
+            rpre[k][i] = (c < NCH && grow >= 0 && col < p.N)
+                             ? *reinterpret_cast<const float4*>(p.residual + (long long)grow * p.ldr + col)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      if (half >= NCH) {   // BN == 32: the odd-parity warps own no chunk but still take part in the hand-back
+        __syncwarp();
+        if (lane == 0) release_acc(acc);
+      }
+      const uint32_t t_row = tmem_base + (uint32_t(lane_grp * 32) << 16) + acc * BN;
+#pragma unroll
+      for (int k = 0; k < MYCH; ++k) {
+        const int c = half + 2 * k;
+        if (c < NCH) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_row + c * 32, v);
+          tmem_ld_wait();
+          if (c + 2 >= NCH) {
+            // last TMEM read of this warp for this accumulator stage -> hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) release_acc(acc);
+          }
+          const int n0 = n_base + c * 32;
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (n0 + j < p.N) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+                f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
               }
-              if (p.residual2 != nullptr) {
-                const float4 r = *reinterpret_cast<const float4*>(p.residual2 + (long long)grow * p.ldr2 + n0 + ch * 4);
-                val.x += r.x; val.y += r.y; val.z += r.z; val.w += r.w;
-              }
-              *reinterpret_cast<float4*>(out + (long long)grow * p.ldo + n0 + ch * 4) = val;
             }
           }
-          __syncwarp();
+          if (p.rowvec != nullptr && my_row >= 0) {
+            const float* rv = p.rowvec + (long long)((my_row / p.rows_per_group) % p.n_groups) * p.ldv;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (n0 + j < p.N) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(rv + n0 + j));
+                f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+              }
+            }
+          }
+          if (p.geglu) {
+            // packed weight rows are interleaved (value, gate) pairs: out[n/2] = value * gelu(gate)
+            // (reference GEGLU: attention.py:97-99, chunk order value-first, exact erf GELU)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = f[2 * j] * gelu_erf(f[2 * j + 1]);
+            uint4* dst = reinterpret_cast<uint4*>(my_stage + lane * 32);   // 16 bf16 = 32 B per row
+            dst[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+            dst[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+            __syncwarp();
+            __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+            const int no0 = n0 / 2;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const int rr = i * 16 + (lane >> 1);
+              const int ch = lane & 1;
+              const int grow = my_rowmap[rr];
+              if (grow >= 0 && no0 + ch * 8 < p.N / 2) {
+                const uint4 val = *reinterpret_cast<const uint4*>(my_stage + rr * 32 + ch * 16);
+                *reinterpret_cast<uint4*>(out + (long long)grow * p.ldo + no0 + ch * 8) = val;
+              }
+            }
+            __syncwarp();
+          } else if (p.out_bf16) {
+            // 32 bf16 = 64 B per row, 16 B chunks XOR-swizzled with (row>>1)&3
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+              const int sw = ch ^ ((lane >> 1) & 3);
+              *reinterpret_cast<uint4*>(my_stage + lane * 64 + sw * 16) =
+                  make_uint4(pack_bf16x2(f[ch * 8 + 0], f[ch * 8 + 1]), pack_bf16x2(f[ch * 8 + 2], f[ch * 8 + 3]),
+                             pack_bf16x2(f[ch * 8 + 4], f[ch * 8 + 5]), pack_bf16x2(f[ch * 8 + 6], f[ch * 8 + 7]));
+            }
+            __syncwarp();
+            __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rr = i * 8 + (lane >> 2);
+              const int ch = lane & 3;
+              const int grow = my_rowmap[rr];
+              if (grow >= 0 && n0 + ch * 8 < p.N) {
+                const int sw = ch ^ ((rr >> 1) & 3);
+                uint4 val = *reinterpret_cast<const uint4*>(my_stage + rr * 64 + sw * 16);
+                if (p.residual != nullptr) {
+                  const float* rp = p.residual + (long long)grow * p.ldr + n0 + ch * 8;
+                  const float4 r0 = *reinterpret_cast<const float4*>(rp);
+                  const float4 r1 = *reinterpret_cast<const float4*>(rp + 4);
+                  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&val);
+                  float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+                  float2 c2 = __bfloat1622float2(h[2]), d = __bfloat1622float2(h[3]);
+                  val = make_uint4(pack_bf16x2(a.x + r0.x, a.y + r0.y), pack_bf16x2(b.x + r0.z, b.y + r0.w),
+                                   pack_bf16x2(c2.x + r1.x, c2.y + r1.y), pack_bf16x2(d.x + r1.z, d.y + r1.w));
+                }
+                *reinterpret_cast<uint4*>(out + (long long)grow * p.ldo + n0 + ch * 8) = val;
+              }
+            }
+            __syncwarp();
+          } else {
+            // 32 fp32 = 128 B per row, 16 B chunks XOR-swizzled with row&7 (conflict-free both ways)
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+              const int sw = ch ^ (lane & 7);
+              *reinterpret_cast<float4*>(my_stage + lane * 128 + sw * 16) =
+                  make_float4(f[ch * 4 + 0], f[ch * 4 + 1], f[ch * 4 + 2], f[ch * 4 + 3]);
+            }
+            __syncwarp();
+            float* out = reinterpret_cast<float*>(p.out);
+            const int ch = lane & 7;
+            const bool col_ok = n0 + ch * 4 < p.N;
+            float4 r2[8];
+            if (p.residual2 != nullptr) {
+              // second addend: all eight loads are issued before the first store (out may alias a residual)
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int grow = my_rowmap[i * 4 + (lane >> 3)];
+                r2[i] = (grow >= 0 && col_ok)
+                            ? *reinterpret_cast<const float4*>(p.residual2 + (long long)grow * p.ldr2 + n0 + ch * 4)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = i * 4 + (lane >> 3);
+              const int grow = my_rowmap[rr];
+              if (grow >= 0 && col_ok) {
+                const int sw = ch ^ (rr & 7);
+                float4 val = *reinterpret_cast<const float4*>(my_stage + rr * 128 + sw * 16);
+                if (pre) {
+                  float4 rr4;
+                  if (k < PRECH) rr4 = rpre[k < PRECH ? k : 0][i];
+                  else rr4 = *reinterpret_cast<const float4*>(p.residual + (long long)grow * p.ldr + n0 + ch * 4);
+                  val.x += rr4.x; val.y += rr4.y; val.z += rr4.z; val.w += rr4.w;
+                }
+                if (p.residual2 != nullptr) { val.x += r2[i].x; val.y += r2[i].y; val.z += r2[i].z; val.w += r2[i].w; }
+                *reinterpret_cast<float4*>(out + (long long)grow * p.ldo + n0 + ch * 4) = val;
+              }
+            }
+            __syncwarp();
+          }
         }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -309,16 +390,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all();   // the leader's MMAs read the peer's smem/TMEM: nobody leaves early
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (NCTA == 2) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+static int gemm_mode_override() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("PN_GEMM_MODE");
+    mode = e ? atoi(e) : 0;
+  }
+  return mode;
+}
+
 // Pick the [tn, th, tw] box (product 128, powers of two) that wastes the fewest MMA rows.
 static void pick_tile(long long NB, long long H, long long W, int* tw, int* th, int* tn) {
   double best = 1e30;
@@ -334,18 +426,33 @@ static void pick_tile(long long NB, long long H, long long W, int* tw, int* th, 
   }
 }
 
-template <int BN, int STAGES>
-static int launch_gemm(const GemmParams& p, int num_tiles, cudaStream_t stream) {
-  using S = GemmSmem<BN, STAGES>;
+template <int BN, int STAGES, int NCTA>
+static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
+  using S = GemmSmem<BN, STAGES, NCTA>;
+  static_assert(S::TOTAL <= 232448, "shared memory budget exceeded");
   static bool attr_set = false;
   if (!attr_set) {
-    PN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    PN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     attr_set = true;
   }
-  int grid = sm_count();
-  if (grid > num_tiles) grid = num_tiles;
-  gemm_tc_kernel<BN, STAGES><<<grid, GEMM_THREADS, S::TOTAL, stream>>>(p);
-  PN_CHECK_CUDA(cudaGetLastError());
+  const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int num_tiles = ((tiles_m + NCTA - 1) / NCTA) * p.tiles_col;
+  int units = sm_count() / NCTA;
+  if (units > num_tiles) units = num_tiles;
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(units * NCTA);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = S::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NCTA;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, NCTA>, p));
   return PN_OK;
 }
 
@@ -399,10 +506,15 @@ extern "C" int pn_gemm(const pn_gemm_args* a, void* stream_v) {
   p.n_groups = a->n_groups > 0 ? a->n_groups : 1;
   p.out_bf16 = a->out_bf16; p.geglu = a->geglu;
 
-  // N tile: every channel count of the network is a multiple of 160 (320/640/960/1280/1920/2560/5120);
-  // fall back to 128 / 64 / 32 otherwise.
-  int BN;
-  if (a->N % 160 == 0) BN = 160;
+  // Tile selection. Big problems run on CTA pairs (cta_group::2, 256 x BN tiles: the weight tile is fetched once per
+  // pair, which is what lifts the L2->SM-bound K loop); small ones keep single-CTA 128 x BN tiles for parallelism.
+  // Every channel count of the network is a multiple of 160 (320/640/960/1280/1920/2560/5120/10240).
+  const long long tiles_m_1 = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
+  int BN, NCTA = 1;
+  const int force = gemm_mode_override();     // PN_GEMM_MODE=1|2 (debug / A-B measurements)
+  if (a->N % 256 == 0 && (force == 2 || (force == 0 && tiles_m_1 * (a->N / 256) >= 2 * sm_count()))) { BN = 256; NCTA = 2; }
+  else if (a->N % 160 == 0 && (force == 2 || (force == 0 && tiles_m_1 * (a->N / 160) >= 2 * sm_count()))) { BN = 160; NCTA = 2; }
+  else if (a->N % 160 == 0) BN = 160;
   else if (a->N >= 128) BN = 128;
   else if (a->N > 32) BN = 64;
   else BN = 32;
@@ -416,16 +528,16 @@ extern "C" int pn_gemm(const pn_gemm_args* a, void* stream_v) {
   const uint64_t K = (uint64_t)a->taps_h * a->taps_w * a->C;
   const uint64_t dimsB[2] = {K, (uint64_t)a->N};
   const uint64_t strB[1] = {K};
-  const uint32_t boxB[2] = {64u, (uint32_t)BN};
+  const uint32_t boxB[2] = {64u, (uint32_t)(BN / NCTA)};
   rc = cached_tmap_bf16(&p.mapB, a->B, 2, dimsB, strB, boxB, 128);
   if (rc != PN_OK) return rc;
 
-  const int num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_col;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  if (NCTA == 2) return BN == 256 ? launch_gemm<256, 5, 2>(p, stream) : launch_gemm<160, 6, 2>(p, stream);
   switch (BN) {
-    case 160: return launch_gemm<160, 5>(p, num_tiles, stream);
-    case 128: return launch_gemm<128, 6>(p, num_tiles, stream);
-    case 64: return launch_gemm<64, 8>(p, num_tiles, stream);
-    default: return launch_gemm<32, 8>(p, num_tiles, stream);
+    case 160: return launch_gemm<160, 5, 1>(p, stream);
+    case 128: return launch_gemm<128, 6, 1>(p, stream);
+    case 64: return launch_gemm<64, 8, 1>(p, stream);
+    default: return launch_gemm<32, 8, 1>(p, stream);
   }
 }

@@ -21,11 +21,9 @@ constexpr int GN_CHUNK = 64;  // pixels per partial-statistics block
 // partial[f][chunk][g][2] = (sum, sumsq) over the chunk's pixels x group channels (fp32, <= 64*cpg terms each)
 __global__ void __launch_bounds__(256) gn_partial_kernel(const float* __restrict__ x, float* __restrict__ partial,
                                                          int P, int C, int nchunks) {
-  __shared__ float bins[GN_GROUPS * 2];
+  extern __shared__ float colacc[];   // [2][C]: per-channel sum / sum of squares of this pixel chunk
   const int f = blockIdx.y, chunk = blockIdx.x;
   const int cpg = C / GN_GROUPS;
-  if (threadIdx.x < GN_GROUPS * 2) bins[threadIdx.x] = 0.f;
-  __syncthreads();
   const int p0 = chunk * GN_CHUNK;
   const int p1 = min(P, p0 + GN_CHUNK);
   const int c4n = C / 4;
@@ -39,16 +37,18 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const float* __restrict
       s[2] += v.z; q[2] += v.z * v.z;
       s[3] += v.w; q[3] += v.w * v.w;
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int g = (c4 * 4 + j) / cpg;
-      atomicAdd(&bins[g * 2], s[j]);
-      atomicAdd(&bins[g * 2 + 1], q[j]);
-    }
+    *reinterpret_cast<float4*>(colacc + c4 * 4) = make_float4(s[0], s[1], s[2], s[3]);
+    *reinterpret_cast<float4*>(colacc + C + c4 * 4) = make_float4(q[0], q[1], q[2], q[3]);
   }
   __syncthreads();
-  if (threadIdx.x < GN_GROUPS * 2)
-    partial[((size_t)f * nchunks + chunk) * GN_GROUPS * 2 + threadIdx.x] = bins[threadIdx.x];
+  // fixed-order reduction over the group's channels: bit-reproducible (no atomics)
+  if (threadIdx.x < GN_GROUPS * 2) {
+    const int g = threadIdx.x >> 1, which = threadIdx.x & 1;
+    const float* src = colacc + which * C + g * cpg;
+    float acc = 0.f;
+    for (int j = 0; j < cpg; ++j) acc += src[j];
+    partial[((size_t)f * nchunks + chunk) * GN_GROUPS * 2 + threadIdx.x] = acc;
+  }
 }
 
 // scale[f][c] = rstd*gamma[c]; shift[f][c] = beta[c] - mean*rstd*gamma[c]   (double-precision combine)
@@ -239,7 +239,7 @@ extern "C" int pn_groupnorm_silu(const float* x, const float* gamma, const float
   float* partial = workspace;
   float* scale = workspace + (size_t)F * nchunks * GN_GROUPS * 2;
   float* shift = scale + (size_t)F * C;
-  gn_partial_kernel<<<dim3(nchunks, F), 256, 0, st>>>(x, partial, P, C, nchunks);
+  gn_partial_kernel<<<dim3(nchunks, F), 256, 2 * C * sizeof(float), st>>>(x, partial, P, C, nchunks);
   PN_CHECK_CUDA(cudaGetLastError());
   gn_finalize_kernel<<<F, 256, 0, st>>>(partial, gamma, beta, scale, shift, P, C, nchunks, eps);
   PN_CHECK_CUDA(cudaGetLastError());

@@ -109,7 +109,7 @@ def test_zero_init_model_predicts_zero_and_cross_view_table():
     Fr, H, wv, heads = 1, 8, 16, 2
     qkv = torch.randn(Fr, H, 6, wv, 3 * 128, device="cuda").to(torch.bfloat16)
     base = ops.attention_view(qkv, heads, True, CROSS_VIEW_NEIGHBOURS)
-    expect = {0: {1, 5}, 1: {0, 2}, 2: {1, 3}, 3: {2, 4}, 4: {3, 5}, 5: {0, 4}}   # who attends view j's K/V
+    expect = {0: {1}, 1: {0, 2}, 2: {1, 3}, 3: {2, 4}, 4: {3, 5}, 5: {0, 4}}   # {v : j in neighbours[v]} — view 5 sees {4} only
     for j in range(6):
         q2 = qkv.clone()
         q2[:, :, j, :, 128:] += 1.0                        # perturb K and V of view j only
