@@ -223,7 +223,8 @@ def run_ours(args) -> None:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    seed = 3407 + rank                                             # inference.py:250
+    from panacea_b200 import dist_utils as D
+    seed = D.rank_seed(rank)                                       # inference.py:250: 3407 + rank
     log("building full-size UNet + ControlNet on the device")
     pipe = build_pipeline(dev, seed)
     log("synthetic host inputs (pinned)")
@@ -281,10 +282,7 @@ def run_ours(args) -> None:
     ms = ev0.elapsed_time(ev1)
     log(f"timed region: {K} steps in {ms:.1f} ms")
     clk = clocks.stop() if rank == 0 else None
-    if dist is not None:
-        tms = torch.tensor([ms], device=dev)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = tms.item()
+    ms = D.max_over_ranks(ms, dev)
 
     # ---- timed region 2: end to end through the public API with host buffers (`e2e`)
     xh = torch.empty(n, 4, H, VIEWS * W_VIEW).pin_memory()
@@ -316,13 +314,11 @@ def run_ours(args) -> None:
         dist.barrier()
     ms_e2e = e0.elapsed_time(e1)
     log(f"e2e region: {K} steps in {ms_e2e:.1f} ms")
-    if dist is not None:
-        tms = torch.tensor([ms_e2e], device=dev)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms_e2e = tms.item()
-        # configs[2]: gather the final latents on rank 0 (stand-in for decoded frames; the VAE is out of scope)
-        outs = [torch.empty_like(x) for _ in range(world)] if rank == 0 else None
-        dist.gather(x, outs, dst=0)
+    ms_e2e = D.max_over_ranks(ms_e2e, dev)
+    # configs[2]: gather the final latents on rank 0 over NCCL (stand-in for decoded frames; the VAE is out of scope)
+    gathered = D.gather_on_rank0(x)
+    if rank == 0:
+        log(f"gathered {len(gathered)} latent tensors of shape {tuple(x.shape)} on rank 0")
 
     # ---- dominant-kernel roofline (eager, per-launch CUDA events), launch count of one graphed eps-eval
     flops, secs, n_gemm = profile_dominant_kernel(pipe, x_in, t_all[0], cc2)

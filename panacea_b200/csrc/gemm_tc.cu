@@ -60,8 +60,9 @@ struct GemmSmem {
   static constexpr int TOTAL = STAGES * STAGE_BYTES + STAGING_BYTES + ROWMAP_BYTES + BAR_BYTES + 1024;
 };
 
-template <int BN, int STAGES, int NCTA>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+// MODE: 0 = fp32 store (+ up to two fp32 residuals), 1 = bf16 store, 2 = GEGLU (bf16 store of N/2 columns)
+template <int BN, int STAGES, int NCTA, int MODE>
+__global__ void __maxnreg__(200) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using S = GemmSmem<BN, STAGES, NCTA>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       const int n_base = tcol * BN;
       // ---- residual prefetch (fp32 output path): lane -> (row i*4 + lane/8, 16-byte column chunk lane%8)
       float4 rpre[PRECH][8];
-      const bool pre = (p.residual != nullptr) && !p.out_bf16;
+      const bool pre = (MODE == 0) && (p.residual != nullptr);
       if (pre) {
 #pragma unroll
         for (int k = 0; k < PRECH; ++k) {
@@ -286,11 +287,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
               }
             }
           }
-          if (p.geglu) {
+          if (MODE == 2) {
             // packed weight rows are interleaved (value, gate) pairs: out[n/2] = value * gelu(gate)
             // (reference GEGLU: attention.py:97-99, chunk order value-first, exact erf GELU)
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = f[2 * j] * gelu_erf(f[2 * j + 1]);
+            for (int j = 0; j < 16; ++j) f[j] = f[2 * j] * gelu_erf_fast(f[2 * j + 1]);
             uint4* dst = reinterpret_cast<uint4*>(my_stage + lane * 32);   // 16 bf16 = 32 B per row
             dst[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
             dst[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
               }
             }
             __syncwarp();
-          } else if (p.out_bf16) {
+          } else if (MODE == 1) {
             // 32 bf16 = 64 B per row, 16 B chunks XOR-swizzled with (row>>1)&3
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
@@ -426,13 +427,13 @@ static void pick_tile(long long NB, long long H, long long W, int* tw, int* th, 
   }
 }
 
-template <int BN, int STAGES, int NCTA>
-static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
+template <int BN, int STAGES, int NCTA, int MODE>
+static int launch_gemm_mode(const GemmParams& p, cudaStream_t stream) {
   using S = GemmSmem<BN, STAGES, NCTA>;
   static_assert(S::TOTAL <= 232448, "shared memory budget exceeded");
   static bool attr_set = false;
   if (!attr_set) {
-    PN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    PN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, NCTA, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     attr_set = true;
   }
   const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
@@ -452,8 +453,15 @@ static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  PN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, NCTA>, p));
+  PN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, NCTA, MODE>, p));
   return PN_OK;
+}
+
+template <int BN, int STAGES, int NCTA>
+static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
+  if (p.geglu) return launch_gemm_mode<BN, STAGES, NCTA, 2>(p, stream);
+  if (p.out_bf16) return launch_gemm_mode<BN, STAGES, NCTA, 1>(p, stream);
+  return launch_gemm_mode<BN, STAGES, NCTA, 0>(p, stream);
 }
 
 }  // namespace pn

@@ -1,0 +1,57 @@
+"""Runs one launch of each hot kernel at its headline shape inside a cudaProfilerStart/Stop range, for
+  ncu --set full --import-source on --clock-control none --profile-from-start off -o gpurun_out/prof python tools/profile_kernels.py
+"""
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from panacea_b200.ops import NativeOps  # noqa: E402
+
+BF16 = torch.bfloat16
+NEIGH = ((5, 1), (0, 2), (1, 3), (2, 4), (3, 5), (4,))
+
+
+def main():
+    ops = NativeOps()
+    dev = "cuda"
+    BT, H, W, C = 16, 32, 336, 320
+    M = BT * H * W
+    x = torch.randn(M, C, device=dev).to(BF16)
+    res = torch.randn(M, C, device=dev)
+    w = (torch.randn(C, C, device=dev) * C ** -0.5).to(BF16)
+    w8 = (torch.randn(8 * C, C, device=dev) * C ** -0.5).to(BF16)
+    b8 = torch.randn(8 * C, device=dev)
+    bias = torch.randn(C, device=dev)
+    wc = (torch.randn(C, 9 * C, device=dev) * (9 * C) ** -0.5).to(BF16)
+    h4 = torch.randn(M, 4 * C, device=dev).to(BF16)
+    w4 = (torch.randn(C, 4 * C, device=dev) * (4 * C) ** -0.5).to(BF16)
+    qkv = torch.randn(BT, H, 6, W // 6, 3 * C, device=dev).to(BF16)
+    x2 = torch.randn(M // 16, 1280, device=dev).to(BF16)
+    wc2 = (torch.randn(1280, 9 * 1280, device=dev) * (9 * 1280) ** -0.5).to(BF16)
+    b2 = torch.randn(1280, device=dev)
+    g = torch.ones(C, device=dev); bz = torch.zeros(C, device=dev)
+
+    def run_all():
+        ops.gemm(x.view(BT, H, W, C), wc, bias=bias, taps=(3, 3))                       # conv3x3 level 0
+        ops.gemm(x2.view(BT, H // 4, W // 4, 1280), wc2, bias=b2, taps=(3, 3))          # conv3x3 level 2
+        ops.gemm(x, w, bias=bias, residual=res, out=res)                               # linear + residual (HBM-bound)
+        ops.gemm(x, w8, bias=b8, geglu=True, out_dtype=BF16)                           # ff1 GEGLU
+        ops.gemm(h4, w4, bias=bias, residual=res, out=res)                             # ff2
+        ops.attention_view(qkv, 5, False, NEIGH)                                       # intra-view attention
+        ops.attention_view(qkv, 5, True, NEIGH)                                        # cross-view attention
+        ops.groupnorm(res.view(BT, H * W, C), g, bz, 1e-5, True)
+        ops.layernorm(res, g, bz)
+
+    for _ in range(2):
+        run_all()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    run_all()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+
+
+if __name__ == "__main__":
+    main()
