@@ -96,12 +96,29 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline (oracle)
+def usable_cores() -> int:
+    """Cores this process may really use: affinity mask, cgroup CPU quota, PN_CPU_THREADS override. (nproc can report
+    128 on a box whose container is throttled to a fraction of that; running 128 OpenMP threads there is far slower
+    than running 16.)"""
+    if os.environ.get("PN_CPU_THREADS"):
+        return max(1, int(os.environ["PN_CPU_THREADS"]))
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = Path("/sys/fs/cgroup/cpu.max").read_text().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return max(1, min(n, 32))       # the op mix (thousands of small ops per eval) stops scaling well before 32 threads
+
+
 def cpu_baseline(budget_s: float, steps: int = 1, warmup: int = 0):
     """Times the CPU oracle port (oracle/unet_port.py — the reference algorithm restated in plain PyTorch fp32) on the
-    host cores with all threads, on a bounded sample of the workload. Returns (steps_per_s, description, cores, ms)."""
+    host cores, on a bounded sample of the workload. Returns (steps_per_s, description, cores, ms)."""
     from oracle import unet_port as P
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
+    t_start = time.perf_counter()
     cfg = P.NetConfig()
     spec = P.state_spec(cfg)
     # cheap non-degenerate weights (timing only): tile one random block, scale like the seeded init
@@ -110,7 +127,8 @@ def cpu_baseline(budget_s: float, steps: int = 1, warmup: int = 0):
     sd = {}
     for k, shape in spec.items():
         n = math.prod(shape)
-        v = pool.repeat((n + pool.numel() - 1) // pool.numel())[:n].reshape(shape)
+        v = pool[:n] if n <= pool.numel() else pool.repeat((n + pool.numel() - 1) // pool.numel())[:n]
+        v = v.reshape(shape)
         if k.endswith(".bias"):
             v = v * 0.05
         elif len(shape) == 1:
@@ -118,10 +136,11 @@ def cpu_baseline(budget_s: float, steps: int = 1, warmup: int = 0):
         else:
             v = v * (0.7 / math.sqrt(math.prod(shape[1:])))
         sd[k] = v.contiguous()
+    log(f"cpu baseline: weights ready after {time.perf_counter() - t_start:.1f}s, {cores} threads")
 
-    def run(frames_T: int, b: int, h: int):
+    def run(frames_T: int, b: int, h: int, wv: int = W_VIEW):
         c = P.NetConfig(num_frames=frames_T)
-        BT, Wt = b * frames_T, VIEWS * W_VIEW
+        BT, Wt = b * frames_T, VIEWS * wv
         x = torch.randn(BT, 4, h, Wt)
         cond = {"concat": torch.randn(BT, 4, h, Wt), "cond_feat": torch.rand(BT, 19, 8 * h, 8 * Wt), "crossattn": torch.randn(b, 77, 1024)}
         t = torch.full((BT,), 500, dtype=torch.int64)
@@ -129,23 +148,30 @@ def cpu_baseline(budget_s: float, steps: int = 1, warmup: int = 0):
         P.wrapper_forward(sd, c, x, t, cond)
         return time.perf_counter() - t0
 
-    # calibrate with the smallest sample (single frame, half the latent rows), then pick the largest that fits
-    t_cal = run(1, 1, H // 2)
-    per_step_budget = max(budget_s / max(steps + warmup, 1), 1.0)
-    ladder = [("one CFG half (1 sequence x 8 frames, full 32x336 latent); a step is 2 of these", 8, 1, H, 2.0, 8.0),
-              ("one frame (T=1, b=1, full 32x336 latent); a step is 16 of these (pessimistic: CPU efficiency drops at T=1)", 1, 1, H, 16.0, 2.0),
-              ("one frame at half height (T=1, b=1, 16x336 latent); a step is 32 of these", 1, 1, H // 2, 32.0, 1.0)]
+    # calibrate on a tiny frame (8 x 6*8 latent, 1/28 of the pixels of a full frame), then pick the largest sample whose
+    # predicted cost fits the per-step budget. Cost model: linear in pixels with the measured T=8 / T=1 batching gain.
+    t_tiny = run(1, 1, 8, 8)
+    log(f"cpu baseline: calibration eval (1 frame, 8x48 latent) {t_tiny:.2f}s")
+    per_step_budget = max((budget_s - (time.perf_counter() - t_start)) / max(steps + warmup, 1), 1.0)
+    pix_full = H * W_VIEW / 64.0                       # full frame / tiny frame pixel ratio (28x)
+    ladder = [("one CFG half (1 sequence x 8 frames, full 32x336 latent); a step is 2 of these", 8, 1, H, W_VIEW, 2.0, 8 * pix_full * 0.5),
+              ("one frame (T=1, b=1, full 32x336 latent); a step is 16 of these", 1, 1, H, W_VIEW, 16.0, pix_full),
+              ("one frame at half height (T=1, b=1, 16x336 latent); a step is 32 of these", 1, 1, H // 2, W_VIEW, 32.0, pix_full / 2),
+              ("one frame at 8x336 latent (T=1, b=1); a step is 64 of these", 1, 1, 8, W_VIEW, 64.0, pix_full / 4),
+              ("one frame at 8x48 latent (T=1, b=1, 8 columns per view); a step is 448 of these", 1, 1, 8, 8, 16.0 * pix_full, 1.0)]
     choice = ladder[-1]
     for item in ladder:
-        if t_cal * item[5] * 1.3 <= per_step_budget:
+        if t_tiny * item[6] * 1.2 <= per_step_budget:
             choice = item
             break
-    desc, fT, b, h, per_step, _ = choice
+    desc, fT, b, h, wv, per_step, _ = choice
+    log(f"cpu baseline: sample = {desc}")
     for _ in range(warmup):
-        run(fT, b, h)
-    times = [run(fT, b, h) for _ in range(max(steps, 1))]
+        run(fT, b, h, wv)
+    times = [run(fT, b, h, wv) for _ in range(max(steps, 1))]
     t_mean = sum(times) / len(times)
-    return 1.0 / (per_step * t_mean), f"{desc}; torch {torch.__version__} fp32, {cores} threads", cores, t_mean * 1e3
+    return (1.0 / (per_step * t_mean), f"{desc}; torch {torch.__version__} fp32, {cores} threads (nproc {os.cpu_count()})",
+            cores, t_mean * 1e3)
 
 
 def run_reference(args) -> None:
