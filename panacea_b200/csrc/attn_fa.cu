@@ -97,10 +97,10 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
     for (int i = 0; i < FA_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&kv_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 256);
-      mbar_init(&p_full[i], 256);
+      mbar_init(&s_empty[i], 8);      // one elected arrive per softmax warp (256 per-thread arrives on one
+      mbar_init(&p_full[i], 8);       // mbarrier serialise in shared memory)
       mbar_init(&pv_full[i], 1);
-      mbar_init(&pv_empty[i], 256);
+      mbar_init(&pv_empty[i], 8);
     }
     fence_barrier_init();
   }
@@ -211,7 +211,8 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
 #pragma unroll
       for (int t = 0; t < 32; ++t) O[t] = O[t] * alpha + __uint_as_float(v[t]);
       tc_fence_before();
-      mbar_arrive(&pv_empty[buf]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&pv_empty[buf]);
     };
 
     for (int j = 0; j < nblk; ++j) {
@@ -228,7 +229,8 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
       }
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(&s_empty[buf]);                 // S buffer may be overwritten by the MMA of block j+2
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[buf]);  // S buffer may be overwritten by the MMA of block j+2
       float mx = -INFINITY;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -267,8 +269,9 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
               make_uint4(pack_bf16x2(e[8], e[9]), pack_bf16x2(e[10], e[11]), pack_bf16x2(e[12], e[13]), pack_bf16x2(e[14], e[15]));
         }
       }
-      fence_proxy_async_smem();
-      mbar_arrive(&p_full[buf]);
+      fence_proxy_async_smem();                   // every writer publishes its P stores to the async proxy ...
+      __syncwarp();                               // ... before the warp's single arrive
+      if (lane == 0) mbar_arrive(&p_full[buf]);
       l_run = l_run * alpha + rs;
       m_run = m_new;
       if (j > 0) consume_pv(j - 1, alpha_prev);

@@ -62,7 +62,7 @@ struct GemmSmem {
 
 // MODE: 0 = fp32 store (+ up to two fp32 residuals), 1 = bf16 store, 2 = GEGLU (bf16 store of N/2 columns)
 template <int BN, int STAGES, int NCTA, int MODE>
-__global__ void __maxnreg__(192) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using S = GemmSmem<BN, STAGES, NCTA>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
