@@ -27,19 +27,18 @@ constexpr int FA_D = 64;
 constexpr int FA_STAGES = 3;
 constexpr int FA_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 softmax
 constexpr int FA_TILE_BYTES = 128 * 128;          // 128 rows x 64 bf16
-constexpr int FA_SMEM_Q = 0;
-constexpr int FA_SMEM_K = FA_TILE_BYTES;
+constexpr int FA_SMEM_Q = 0;                                        // 2 query tiles (double buffered across tiles)
+constexpr int FA_SMEM_K = 2 * FA_TILE_BYTES;
 constexpr int FA_SMEM_V = FA_SMEM_K + FA_STAGES * FA_TILE_BYTES;
 constexpr int FA_SMEM_P = FA_SMEM_V + FA_STAGES * FA_TILE_BYTES;   // 2 buffers x 2 atoms x 16 KB
 constexpr int FA_SMEM_BAR = FA_SMEM_P + 4 * FA_TILE_BYTES;
-constexpr int FA_SMEM_XCH = FA_SMEM_BAR + 256;                      // row-max / row-sum exchange: [2][2][128] floats
-constexpr int FA_SMEM_TOTAL = FA_SMEM_XCH + 2 * 2 * 128 * 4 + 1024;
+constexpr int FA_SMEM_XCH = FA_SMEM_BAR + 256;                      // row-max exchange [2][2][128] + row-sum exchange [2][128]
+constexpr int FA_SMEM_TOTAL = FA_SMEM_XCH + (2 * 2 * 128 + 2 * 128) * 4 + 1024;
 
 struct FaParams {
   CUtensorMap mapQ;
   CUtensorMap mapK;
   CUtensorMap mapV;
-  int q_ch0, k_ch0, v_ch0;     // channel offset of head 0 inside a token row
   int heads;
   int F, H, V, W;              // query token grid
   int qw, qh, tiles_x, tiles_y;
@@ -47,43 +46,55 @@ struct FaParams {
   int kv_views[8][2];
   int kv_view_count[8];
   int kv_frame_div;            // kv frame = q frame / kv_frame_div
+  int total_tiles;
   float scale_log2;            // softmax scale * log2(e)
   __nv_bfloat16* out;
   long long out_ld;            // token stride of out (elements)
-  int out_ch0;
 };
 
+struct FaTile {
+  int x0, y0, head, view, frame, nblk;
+};
+
+// q tile fastest, then head, view, frame: CTAs that run concurrently share K/V in L2
+__device__ __forceinline__ FaTile fa_decode(const FaParams& p, int tile) {
+  FaTile t;
+  const int tx = tile % p.tiles_x; tile /= p.tiles_x;
+  const int ty = tile % p.tiles_y; tile /= p.tiles_y;
+  t.head = tile % p.heads; tile /= p.heads;
+  t.view = tile % p.V; tile /= p.V;
+  t.frame = tile;
+  t.x0 = tx * p.qw;
+  t.y0 = ty * p.qh;
+  t.nblk = p.kv_view_count[t.view] * p.kv_yblocks;
+  return t;
+}
+
+// Persistent kernel: each CTA walks a strided list of query tiles; the K/V-block pipeline (S and PV double buffers,
+// 3-stage K/V ring) runs ACROSS tile boundaries, so the prologue, the Q load and the last PV of a tile hide behind the
+// next tile's work (this is what makes the 1-block text attention and the 16-block view attention share one kernel).
+// MASK: the key block has padding columns (kv_rows < kv_n, e.g. 77 text keys in an 80-wide block) that must get p = 0.
+template <bool MASK>
 __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_constant__ FaParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FA_SMEM_BAR);
-  uint64_t* q_full = bars;                     // [1]
-  uint64_t* k_full = bars + 1;                 // [3]
-  uint64_t* v_full = bars + 4;                 // [3]
-  uint64_t* kv_empty = bars + 7;               // [3]
-  uint64_t* s_full = bars + 10;                // [2]
-  uint64_t* s_empty = bars + 12;               // [2]
-  uint64_t* p_full = bars + 14;                // [2]
-  uint64_t* pv_full = bars + 16;               // [2]
-  uint64_t* pv_empty = bars + 18;              // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* q_full = bars;                     // [2]
+  uint64_t* q_empty = bars + 2;                // [2]
+  uint64_t* k_full = bars + 4;                 // [3]
+  uint64_t* v_full = bars + 7;                 // [3]
+  uint64_t* kv_empty = bars + 10;              // [3]
+  uint64_t* s_full = bars + 13;                // [2]
+  uint64_t* s_empty = bars + 15;               // [2]
+  uint64_t* p_full = bars + 17;                // [2]
+  uint64_t* pv_full = bars + 19;               // [2]
+  uint64_t* pv_empty = bars + 21;              // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 23);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // tile decode: q tile fastest so that concurrently resident CTAs share K/V in L2
-  int bid = blockIdx.x;
-  const int tx = bid % p.tiles_x; bid /= p.tiles_x;
-  const int ty = bid % p.tiles_y; bid /= p.tiles_y;
-  const int head = bid % p.heads; bid /= p.heads;
-  const int view = bid % p.V; bid /= p.V;
-  const int frame = bid;
-  const int x0 = tx * p.qw, y0 = ty * p.qh;
-  const int nviews = p.kv_view_count[view];
-  const int nblk = nviews * p.kv_yblocks;
-  const int kv_frame = frame / p.kv_frame_div;
-
-  // zero K/V/Q staging once: rows a TMA box does not cover (kv_rows..kv_n) must read as 0, never as stale NaNs
+  // zero Q/K/V staging once: rows a TMA box does not cover (kv_rows..kv_n) must read as 0, never as stale NaNs
   {
     uint4* z = reinterpret_cast<uint4*>(smem);
     for (int i = threadIdx.x; i < FA_SMEM_P / 16; i += FA_THREADS) z[i] = make_uint4(0, 0, 0, 0);
@@ -93,12 +104,12 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
     tma_prefetch_desc(&p.mapQ);
     tma_prefetch_desc(&p.mapK);
     tma_prefetch_desc(&p.mapV);
-    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
     for (int i = 0; i < FA_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&kv_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 8);      // one elected arrive per softmax warp (256 per-thread arrives on one
-      mbar_init(&p_full[i], 8);       // mbarrier serialise in shared memory)
+      mbar_init(&s_empty[i], 8);      // one elected arrive per softmax warp
+      mbar_init(&p_full[i], 8);
       mbar_init(&pv_full[i], 1);
       mbar_init(&pv_empty[i], 8);
     }
@@ -117,30 +128,31 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
     if (lane == 0) {
       const uint32_t q_bytes = (uint32_t)(p.qw * p.qh) * 128u;
       const uint32_t kv_bytes = (uint32_t)p.kv_rows * 128u;
-      mbar_arrive_expect_tx(q_full, q_bytes);
-      tma_load_5d(smem + FA_SMEM_Q, &p.mapQ, q_full, p.q_ch0 + head * FA_D, x0, view, y0, frame);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int i = 0; i < nblk; ++i) {
-        const int vi = i / p.kv_yblocks, yb = i - vi * p.kv_yblocks;
-        const int kvv = p.kv_views[view][vi];
-        mbar_wait(&kv_empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&k_full[stage], kv_bytes);
-        tma_load_5d(smem + FA_SMEM_K + stage * FA_TILE_BYTES, &p.mapK, &k_full[stage], p.k_ch0 + head * FA_D, 0, kvv,
-                    yb * p.kh, kv_frame);
-        mbar_arrive_expect_tx(&v_full[stage], kv_bytes);
-        tma_load_5d(smem + FA_SMEM_V + stage * FA_TILE_BYTES, &p.mapV, &v_full[stage], p.v_ch0 + head * FA_D, 0, kvv,
-                    yb * p.kh, kv_frame);
-        if (++stage == FA_STAGES) { stage = 0; phase ^= 1; }
+      int g = 0, it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const FaTile t = fa_decode(p, tile);
+        const int qb = it & 1;
+        mbar_wait(&q_empty[qb], (uint32_t)(((it >> 1) & 1) ^ 1));
+        mbar_arrive_expect_tx(&q_full[qb], q_bytes);
+        tma_load_5d(smem + FA_SMEM_Q + qb * FA_TILE_BYTES, &p.mapQ, &q_full[qb], t.head * FA_D, t.x0, t.view, t.y0, t.frame);
+        const int kv_frame = t.frame / p.kv_frame_div;
+        for (int j = 0; j < t.nblk; ++j, ++g) {
+          const int st = g % FA_STAGES;
+          const int vi = j / p.kv_yblocks, yb = j - vi * p.kv_yblocks;
+          const int kvv = p.kv_views[t.view][vi];
+          mbar_wait(&kv_empty[st], (uint32_t)(((g / FA_STAGES) & 1) ^ 1));
+          mbar_arrive_expect_tx(&k_full[st], kv_bytes);
+          tma_load_5d(smem + FA_SMEM_K + st * FA_TILE_BYTES, &p.mapK, &k_full[st], t.head * FA_D, 0, kvv, yb * p.kh, kv_frame);
+          mbar_arrive_expect_tx(&v_full[st], kv_bytes);
+          tma_load_5d(smem + FA_SMEM_V + st * FA_TILE_BYTES, &p.mapV, &v_full[st], t.head * FA_D, 0, kvv, yb * p.kh, kv_frame);
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== UMMA issuer =====================
     const uint32_t idesc_s = umma_idesc_bf16(128, p.kv_n, 0, 0);      // S = Q K^T : both K-major
     const uint32_t idesc_pv = umma_idesc_bf16(128, FA_D, 0, 1);       // PV: A = P K-major, B = V MN-major
-    const uint32_t sQ = smem_u32(smem + FA_SMEM_Q);
     const int ksteps_pv = p.kv_n / 16;
-    mbar_wait(q_full, 0);
     auto issue_pv = [&](int i) {
       const int st = i % FA_STAGES, buf = i & 1;
       mbar_wait(&v_full[st], (uint32_t)((i / FA_STAGES) & 1));
@@ -160,37 +172,46 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
       }
       __syncwarp();
     };
-    for (int j = 0; j < nblk; ++j) {
-      const int st = j % FA_STAGES, buf = j & 1;
-      mbar_wait(&k_full[st], (uint32_t)((j / FA_STAGES) & 1));
-      mbar_wait(&s_empty[buf], (uint32_t)(((j >> 1) & 1) ^ 1));
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t sK = smem_u32(smem + FA_SMEM_K + st * FA_TILE_BYTES);
+    int g = 0, it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const FaTile t = fa_decode(p, tile);
+      const int qb = it & 1;
+      const uint32_t sQ = smem_u32(smem + FA_SMEM_Q + qb * FA_TILE_BYTES);
+      mbar_wait(&q_full[qb], (uint32_t)((it >> 1) & 1));
+      for (int j = 0; j < t.nblk; ++j, ++g) {
+        const int st = g % FA_STAGES, buf = g & 1;
+        mbar_wait(&k_full[st], (uint32_t)((g / FA_STAGES) & 1));
+        mbar_wait(&s_empty[buf], (uint32_t)(((g >> 1) & 1) ^ 1));
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sK = smem_u32(smem + FA_SMEM_K + st * FA_TILE_BYTES);
 #pragma unroll
-        for (int k = 0; k < FA_D / 16; ++k) {
-          const uint64_t da = umma_smem_desc(sQ + k * 32, 16, 1024);
-          const uint64_t db = umma_smem_desc(sK + k * 32, 16, 1024);
-          umma_f16_ss(tm_S + buf * 128, da, db, idesc_s, k > 0 ? 1u : 0u);
+          for (int k = 0; k < FA_D / 16; ++k) {
+            const uint64_t da = umma_smem_desc(sQ + k * 32, 16, 1024);
+            const uint64_t db = umma_smem_desc(sK + k * 32, 16, 1024);
+            umma_f16_ss(tm_S + buf * 128, da, db, idesc_s, k > 0 ? 1u : 0u);
+          }
+          umma_commit(&s_full[buf]);
+          if (j == t.nblk - 1) umma_commit(&q_empty[qb]);   // every S MMA reading this Q tile has retired
         }
-        umma_commit(&s_full[buf]);
+        __syncwarp();
+        if (g > 0) issue_pv(g - 1);
       }
-      __syncwarp();
-      if (j > 0) issue_pv(j - 1);
     }
-    issue_pv(nblk - 1);
+    if (g > 0) issue_pv(g - 1);
   } else {
     // ===================== softmax / output warps =====================
     // Two threads per query row: warps w and w+4 share a TMEM lane quarter; the first takes the even 16-column
     // chunks of S and output channels [0,32), the second the odd chunks and channels [32,64). Each reads its S
     // values from TMEM once (registers), the pair agrees on the running row maximum through shared memory (one
-    // 64-thread named barrier per block), row sums are combined once at the end.
+    // 64-thread named barrier per block), row sums are combined once per tile.
     const int sw_id = warp - 2;
     const int lane_grp = warp & 3;
     const int half = sw_id >> 2;
     const int row = lane_grp * 32 + lane;
     const uint32_t lane_addr = uint32_t(lane_grp * 32) << 16;
     float* xch = reinterpret_cast<float*>(smem + FA_SMEM_XCH);      // [buf][half][row]
+    float* xch_l = xch + 2 * 2 * 128;                               // [half][row]
     float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
     float O[32];
 #pragma unroll
@@ -215,88 +236,108 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
       if (lane == 0) mbar_arrive(&pv_empty[buf]);
     };
 
-    for (int j = 0; j < nblk; ++j) {
-      const int buf = j & 1;
-      mbar_wait(&s_full[buf], (uint32_t)((j >> 1) & 1));
-      tc_fence_after();
-      const uint32_t tS = tm_S + lane_addr + buf * 128;
-      // my chunks of S -> registers (single TMEM pass)
-      uint32_t sv[4][16];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int ch = half + 2 * q;
-        if (ch < nchunk) tmem_ld_32x16(tS + ch * 16, sv[q]);
-      }
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[buf]);  // S buffer may be overwritten by the MMA of block j+2
-      float mx = -INFINITY;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int ch = half + 2 * q;
-        if (ch < nchunk) {
-#pragma unroll
-          for (int t = 0; t < 16; ++t)
-            if (ch * 16 + t < p.kv_rows) mx = fmaxf(mx, __uint_as_float(sv[q][t]));
-        }
-      }
-      float* xb = xch + buf * 256;
-      xb[half * 128 + row] = mx;
+    // combine the pair's partial row sums, normalise and store this thread's 32 channels; then clear O
+    auto finish_tile = [&](const FaTile& t, float l_part) {
       pair_sync();
-      mx = fmaxf(mx, xb[(half ^ 1) * 128 + row]);
-      const float m_new = fmaxf(m_run, mx * c);
-      const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_new);
-      float rs = 0.f;
-      uint8_t* sP = smem + FA_SMEM_P + buf * 2 * FA_TILE_BYTES;
+      xch_l[half * 128 + row] = l_part;
+      pair_sync();
+      const float l_tot = l_part + xch_l[(half ^ 1) * 128 + row];
+      const int yy = row / p.qw, xx = row - yy * p.qw;
+      const int x = t.x0 + xx, y = t.y0 + yy;
+      if (row < p.qw * p.qh && x < p.W && y < p.H) {
+        const float inv = 1.f / l_tot;
+        const long long token = (((long long)t.frame * p.H + y) * p.V + t.view) * p.W + x;
+        __nv_bfloat16* dst = p.out + token * p.out_ld + t.head * FA_D + half * 32;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int ch = half + 2 * q;
-        if (ch < nchunk) {
-          float e[16];
-#pragma unroll
-          for (int t = 0; t < 16; ++t) {
-            const float pv = exp2f(__uint_as_float(sv[q][t]) * c - m_new);
-            e[t] = (ch * 16 + t < p.kv_rows) ? pv : 0.f;
-            rs += e[t];
-          }
-          // 16 keys = 2 chunks of 16 B inside atom (ch/4); chunk index within the 128 B row = (ch%4)*2 + {0,1}
-          uint8_t* atom = sP + (ch >> 2) * FA_TILE_BYTES + row * 128;
-          const int c0 = (ch & 3) * 2;
-          *reinterpret_cast<uint4*>(atom + ((c0 ^ (row & 7)) << 4)) =
-              make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
-          *reinterpret_cast<uint4*>(atom + (((c0 + 1) ^ (row & 7)) << 4)) =
-              make_uint4(pack_bf16x2(e[8], e[9]), pack_bf16x2(e[10], e[11]), pack_bf16x2(e[12], e[13]), pack_bf16x2(e[14], e[15]));
+        for (int i = 0; i < 4; ++i) {
+          *reinterpret_cast<uint4*>(dst + i * 8) =
+              make_uint4(pack_bf16x2(O[i * 8 + 0] * inv, O[i * 8 + 1] * inv), pack_bf16x2(O[i * 8 + 2] * inv, O[i * 8 + 3] * inv),
+                         pack_bf16x2(O[i * 8 + 4] * inv, O[i * 8 + 5] * inv), pack_bf16x2(O[i * 8 + 6] * inv, O[i * 8 + 7] * inv));
         }
       }
-      fence_proxy_async_smem();                   // every writer publishes its P stores to the async proxy ...
-      __syncwarp();                               // ... before the warp's single arrive
-      if (lane == 0) mbar_arrive(&p_full[buf]);
-      l_run = l_run * alpha + rs;
-      m_run = m_new;
-      if (j > 0) consume_pv(j - 1, alpha_prev);
-      alpha_prev = alpha;
-    }
-    consume_pv(nblk - 1, alpha_prev);
-
-    // combine the two partial row sums, normalise and store this thread's 32 channels of the row
-    float* xb = xch + (nblk & 1) * 256;
-    pair_sync();                                  // everyone is past the last max exchange before reuse
-    xb[half * 128 + row] = l_run;
-    pair_sync();
-    const float l_tot = l_run + xb[(half ^ 1) * 128 + row];
-    const int yy = row / p.qw, xx = row - yy * p.qw;
-    const int x = x0 + xx, y = y0 + yy;
-    if (row < p.qw * p.qh && x < p.W && y < p.H) {
-      const float inv = 1.f / l_tot;
-      const long long token = (((long long)frame * p.H + y) * p.V + view) * p.W + x;
-      __nv_bfloat16* dst = p.out + token * p.out_ld + p.out_ch0 + head * FA_D + half * 32;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        *reinterpret_cast<uint4*>(dst + i * 8) =
-            make_uint4(pack_bf16x2(O[i * 8 + 0] * inv, O[i * 8 + 1] * inv), pack_bf16x2(O[i * 8 + 2] * inv, O[i * 8 + 3] * inv),
-                       pack_bf16x2(O[i * 8 + 4] * inv, O[i * 8 + 5] * inv), pack_bf16x2(O[i * 8 + 6] * inv, O[i * 8 + 7] * inv));
+      for (int i = 0; i < 32; ++i) O[i] = 0.f;
+    };
+
+    int g = 0;
+    FaTile prev;
+    prev.x0 = prev.y0 = prev.head = prev.view = prev.frame = prev.nblk = 0;
+    float l_prev = 0.f;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const FaTile t = fa_decode(p, tile);
+      l_prev = l_run;
+      m_run = -INFINITY;
+      l_run = 0.f;
+      for (int j = 0; j < t.nblk; ++j, ++g) {
+        const int buf = g & 1;
+        mbar_wait(&s_full[buf], (uint32_t)((g >> 1) & 1));
+        tc_fence_after();
+        const uint32_t tS = tm_S + lane_addr + buf * 128;
+        // my chunks of S -> registers (single TMEM pass)
+        uint32_t sv[4][16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int ch = half + 2 * q;
+          if (ch < nchunk) tmem_ld_32x16(tS + ch * 16, sv[q]);
+        }
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[buf]);  // S buffer may be overwritten by the MMA of block g+2
+        float mx = -INFINITY;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int ch = half + 2 * q;
+          if (ch < nchunk) {
+#pragma unroll
+            for (int tt = 0; tt < 16; ++tt)
+              if (!MASK || ch * 16 + tt < p.kv_rows) mx = fmaxf(mx, __uint_as_float(sv[q][tt]));
+          }
+        }
+        float* xb = xch + buf * 256;
+        xb[half * 128 + row] = mx;
+        pair_sync();
+        mx = fmaxf(mx, xb[(half ^ 1) * 128 + row]);
+        const float m_new = fmaxf(m_run, mx * c);
+        const float alpha = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run - m_new);
+        float rs = 0.f;
+        uint8_t* sP = smem + FA_SMEM_P + buf * 2 * FA_TILE_BYTES;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int ch = half + 2 * q;
+          if (ch < nchunk) {
+            float e[16];
+#pragma unroll
+            for (int tt = 0; tt < 16; ++tt) {
+              const float pv = ex2_approx(__uint_as_float(sv[q][tt]) * c - m_new);
+              e[tt] = (!MASK || ch * 16 + tt < p.kv_rows) ? pv : 0.f;
+              rs += e[tt];
+            }
+            // 16 keys = 2 chunks of 16 B inside atom (ch/4); chunk index within the 128 B row = (ch%4)*2 + {0,1}
+            uint8_t* atom = sP + (ch >> 2) * FA_TILE_BYTES + row * 128;
+            const int c0 = (ch & 3) * 2;
+            *reinterpret_cast<uint4*>(atom + ((c0 ^ (row & 7)) << 4)) =
+                make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
+            *reinterpret_cast<uint4*>(atom + (((c0 + 1) ^ (row & 7)) << 4)) =
+                make_uint4(pack_bf16x2(e[8], e[9]), pack_bf16x2(e[10], e[11]), pack_bf16x2(e[12], e[13]), pack_bf16x2(e[14], e[15]));
+          }
+        }
+        fence_proxy_async_smem();                   // every writer publishes its P stores to the async proxy ...
+        __syncwarp();                               // ... before the warp's single arrive
+        if (lane == 0) mbar_arrive(&p_full[buf]);
+        l_run = l_run * alpha + rs;
+        m_run = m_new;
+        if (g > 0) {
+          consume_pv(g - 1, alpha_prev);            // block g-1 may be the last block of the previous tile
+          if (j == 0) finish_tile(prev, l_prev);
+        }
+        alpha_prev = alpha;
       }
+      prev = t;
+    }
+    if (g > 0) {
+      consume_pv(g - 1, alpha_prev);
+      finish_tile(prev, l_run);
     }
   }
 
@@ -356,7 +397,6 @@ extern "C" int pn_attention(const pn_attn_args* a, void* stream_v) {
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
   p.out_ld = a->out_ld;
-  p.q_ch0 = 0; p.k_ch0 = 0; p.v_ch0 = 0; p.out_ch0 = 0;
 
   const uint64_t chq = (uint64_t)a->heads * FA_D;
   {
@@ -380,12 +420,16 @@ extern "C" int pn_attention(const pn_attn_args* a, void* stream_v) {
   }
   static bool attr_set = false;
   if (!attr_set) {
-    PN_CHECK_CUDA(cudaFuncSetAttribute(attn_fa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_TOTAL));
+    PN_CHECK_CUDA(cudaFuncSetAttribute(attn_fa_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_TOTAL));
+    PN_CHECK_CUDA(cudaFuncSetAttribute(attn_fa_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_TOTAL));
     attr_set = true;
   }
-  const long long grid = (long long)p.tiles_x * p.tiles_y * a->heads * a->V * a->F;
-  PN_REQUIRE(grid > 0 && grid < (1ll << 31), "pn_attention: grid too large");
-  attn_fa_kernel<<<(unsigned)grid, FA_THREADS, FA_SMEM_TOTAL, reinterpret_cast<cudaStream_t>(stream_v)>>>(p);
+  const long long tiles = (long long)p.tiles_x * p.tiles_y * a->heads * a->V * a->F;
+  PN_REQUIRE(tiles > 0 && tiles < (1ll << 31), "pn_attention: too many query tiles");
+  p.total_tiles = (int)tiles;
+  const int grid = tiles < sm_count() ? (int)tiles : sm_count();
+  if (p.kv_rows < p.kv_n) attn_fa_kernel<true><<<grid, FA_THREADS, FA_SMEM_TOTAL, reinterpret_cast<cudaStream_t>(stream_v)>>>(p);
+  else attn_fa_kernel<false><<<grid, FA_THREADS, FA_SMEM_TOTAL, reinterpret_cast<cudaStream_t>(stream_v)>>>(p);
   PN_CHECK_CUDA(cudaGetLastError());
   return PN_OK;
 }

@@ -9,10 +9,10 @@
 // 455-462 Conv2d(padding=1) on the width-concatenated 6-view image; :418,468-476 Conv1d(k=3,padding=1)).
 // B is the packed weight matrix [N, taps*C] (K-major, bf16). Accumulation is fp32 in TMEM.
 //
-// Kernel structure (persistent, one CTA per SM, 320 threads):
+// Kernel structure (persistent, one CTA per SM, 320 or 448 threads):
 //   warp 0     : TMA producer  (A box [tn,th,tw,64] + B box [BN,64] per k-block, 128B swizzle)
 //   warp 1     : TMEM alloc + UMMA issuer (tcgen05.mma cta_group::1 kind::f16, M=128, N=BN, K=16)
-//   warps 2..9 : epilogue (residual prefetch; tcgen05.ld -> bias/row-vector/GEGLU -> smem transpose -> +residual -> global)
+//   warps 2..  : epilogue (residual prefetch; tcgen05.ld -> bias/row-vector/GEGLU -> smem transpose -> +residual -> global)
 // Pipelines: smem full/empty ring (TMA<->MMA) and a 2-deep TMEM accumulator ring (MMA<->epilogue) so the
 // epilogue of tile i overlaps the main loop of tile i+1.
 #include "common.cuh"
@@ -25,7 +25,9 @@ namespace pn {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle atom row
-constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+// warp 0 TMA, warp 1 MMA, warps 2.. epilogue: 8 warps for the fp32/residual mode (168 registers each), 12 for the
+// ALU-heavy bf16 / GEGLU modes (the register file is granted per 4-warp group: 16 warps x 128 registers)
+constexpr int gemm_threads(int mode) { return mode == 0 ? 320 : 448; }
 
 struct GemmParams {
   CUtensorMap mapA;
@@ -49,23 +51,27 @@ struct GemmParams {
   int geglu;
 };
 
-template <int BN, int STAGES, int NCTA>
+template <int BN, int STAGES, int NCTA, int MODE>
 struct GemmSmem {
+  static constexpr int NEPI = gemm_threads(MODE) / 32 - 2;
+  static constexpr int STAGE_WARP_BYTES = MODE == 0 ? 4096 : 2048;   // 32 rows x (128 | 64) B
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / NCTA) * BK * 2;   // a CTA pair splits the N tile: each CTA stages BN/2 weight rows
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGING_BYTES = 8 * 4096;  // per epilogue warp: 32 rows x 128 B
-  static constexpr int ROWMAP_BYTES = 8 * 32 * 4;  // per epilogue warp
+  static constexpr int STAGING_BYTES = NEPI * STAGE_WARP_BYTES;
+  static constexpr int ROWMAP_BYTES = NEPI * 32 * 4;
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + STAGING_BYTES + ROWMAP_BYTES + BAR_BYTES + 1024;
 };
 
 // MODE: 0 = fp32 store (+ up to two fp32 residuals), 1 = bf16 store, 2 = GEGLU (bf16 store of N/2 columns)
 template <int BN, int STAGES, int NCTA, int MODE>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
-  using S = GemmSmem<BN, STAGES, NCTA>;
+__global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+  using S = GemmSmem<BN, STAGES, NCTA, MODE>;
+  constexpr int NEPI = S::NEPI;
+  constexpr int EG = NEPI / 4;                 // epilogue warps per TMEM lane quarter
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* stage_base = smem;
   uint8_t* staging = smem + STAGES * S::STAGE_BYTES;
   int* rowmap = reinterpret_cast<int*>(staging + S::STAGING_BYTES);
@@ -100,7 +106,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 8 * NCTA);  // one arrive per epilogue warp (of both CTAs of a pair)
+      mbar_init(&tmem_empty[i], NEPI * NCTA);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     fence_barrier_init();
   }
@@ -188,17 +194,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       }
     }
   } else {
-    // ===================== epilogue warps (8): TMEM lane quarter = warp & 3, chunk parity = (warp - 2) / 4 ==========
-    // Two warps share a lane quarter and split the 32-column chunks between them (even / odd). Everything a warp
+    // ===================== epilogue warps: TMEM lane quarter = warp & 3, chunk residue = (warp - 2) / 4 ==========
+    // EG warps share a lane quarter and split the 32-column chunks between them (c mod EG). Everything a warp
     // needs from global memory for its chunks (the fp32 residual) is requested at tile start, before the accumulator
     // is even ready, so the DRAM round trip overlaps the main loop instead of serialising the epilogue.
     const int ew = warp - 2;
     const int lane_grp = warp & 3;
-    const int half = ew >> 2;
-    uint8_t* my_stage = staging + ew * 4096;
+    const int half = ew >> 2;                    // chunk residue class of this warp
+    uint8_t* my_stage = staging + ew * S::STAGE_WARP_BYTES;
     int* my_rowmap = rowmap + ew * 32;
     constexpr int NCH = BN / 32;
-    constexpr int MYCH = (NCH + 1) / 2;
+    constexpr int MYCH = (NCH + EG - 1) / EG;
     constexpr int PRECH = MYCH < 3 ? MYCH : 3;   // chunks whose residual is prefetched at tile start (register budget)
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -233,7 +239,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       if (pre) {
 #pragma unroll
         for (int k = 0; k < PRECH; ++k) {
-          const int c = half + 2 * k;
+          const int c = half + EG * k;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int grow = my_rowmap[i * 4 + (lane >> 3)];
@@ -246,19 +252,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      if (half >= NCH) {   // BN == 32: the odd-parity warps own no chunk but still take part in the hand-back
+      if (half >= NCH) {   // narrow tiles: warps that own no chunk still take part in the hand-back
         __syncwarp();
         if (lane == 0) release_acc(acc);
       }
       const uint32_t t_row = tmem_base + (uint32_t(lane_grp * 32) << 16) + acc * BN;
 #pragma unroll
       for (int k = 0; k < MYCH; ++k) {
-        const int c = half + 2 * k;
+        const int c = half + EG * k;
         if (c < NCH) {
           uint32_t v[32];
           tmem_ld_32x32(t_row + c * 32, v);
           tmem_ld_wait();
-          if (c + 2 >= NCH) {
+          if (c + EG >= NCH) {
             // last TMEM read of this warp for this accumulator stage -> hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
@@ -429,7 +435,7 @@ static void pick_tile(long long NB, long long H, long long W, int* tw, int* th, 
 
 template <int BN, int STAGES, int NCTA, int MODE>
 static int launch_gemm_mode(const GemmParams& p, cudaStream_t stream) {
-  using S = GemmSmem<BN, STAGES, NCTA>;
+  using S = GemmSmem<BN, STAGES, NCTA, MODE>;
   static_assert(S::TOTAL <= 232448, "shared memory budget exceeded");
   static bool attr_set = false;
   if (!attr_set) {
@@ -443,7 +449,7 @@ static int launch_gemm_mode(const GemmParams& p, cudaStream_t stream) {
   cudaLaunchConfig_t cfg;
   std::memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(units * NCTA);
-  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.blockDim = dim3(gemm_threads(MODE));
   cfg.dynamicSmemBytes = S::TOTAL;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

@@ -262,6 +262,18 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_ma
 // ----------------------------------------------------------------------------------------------
 // small math helpers
 // ----------------------------------------------------------------------------------------------
+// one MUFU instruction (exp2f() adds range-scaling multiplies and predicates around it; softmax arguments are <= 0
+// and flushing denormal results to zero is exactly what a probability needs)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// 1024-byte aligned start of the dynamic shared-memory window WITHOUT leaving the shared address space (an integer
+// round trip through uintptr_t makes the compiler fall back to generic LD/ST instead of LDS/STS)
+__device__ __forceinline__ uint8_t* smem_align1024(uint8_t* base) {
+  return base + ((1024u - (smem_u32(base) & 1023u)) & 1023u);
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
