@@ -74,7 +74,10 @@ __device__ __forceinline__ FaTile fa_decode(const FaParams& p, int tile) {
 // 3-stage K/V ring) runs ACROSS tile boundaries, so the prologue, the Q load and the last PV of a tile hide behind the
 // next tile's work (this is what makes the 1-block text attention and the 16-block view attention share one kernel).
 // MASK: the key block has padding columns (kv_rows < kv_n, e.g. 77 text keys in an 80-wide block) that must get p = 0.
-template <bool MASK>
+// NCH: number of 16-column chunks of a key block (kv_n / 16) fixed at compile time for the shapes of the network
+// (7 = 112 keys per block at 32x56 views, 8 = 128 keys at 32x64 views, 5 = the 77 text keys, 2 = the 4x7 middle block);
+// 0 = read it from the parameters (any other shape).
+template <bool MASK, int NCH>
 __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_constant__ FaParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_align1024(smem_raw);
@@ -216,7 +219,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
     float O[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) O[i] = 0.f;
-    const int nchunk = p.kv_n / 16;
+    const int nchunk = NCH > 0 ? NCH : p.kv_n / 16;
     const float c = p.scale_log2;
     const uint32_t bar_id = 1 + lane_grp;
 
@@ -284,23 +287,25 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[buf]);  // S buffer may be overwritten by the MMA of block g+2
-        float mx = -INFINITY;
+        // four independent max chains per chunk (a single 56-long dependent chain would cost ~4 cycles per element)
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int ch = half + 2 * q;
           if (ch < nchunk) {
 #pragma unroll
             for (int tt = 0; tt < 16; ++tt)
-              if (!MASK || ch * 16 + tt < p.kv_rows) mx = fmaxf(mx, __uint_as_float(sv[q][tt]));
+              if (!MASK || ch * 16 + tt < p.kv_rows) mx4[tt & 3] = fmaxf(mx4[tt & 3], __uint_as_float(sv[q][tt]));
           }
         }
+        float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
         float* xb = xch + buf * 256;
         xb[half * 128 + row] = mx;
         pair_sync();
         mx = fmaxf(mx, xb[(half ^ 1) * 128 + row]);
         const float m_new = fmaxf(m_run, mx * c);
         const float alpha = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run - m_new);
-        float rs = 0.f;
+        float rs4[4] = {0.f, 0.f, 0.f, 0.f};
         uint8_t* sP = smem + FA_SMEM_P + buf * 2 * FA_TILE_BYTES;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -311,7 +316,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
             for (int tt = 0; tt < 16; ++tt) {
               const float pv = ex2_approx(__uint_as_float(sv[q][tt]) * c - m_new);
               e[tt] = (!MASK || ch * 16 + tt < p.kv_rows) ? pv : 0.f;
-              rs += e[tt];
+              rs4[tt & 3] += e[tt];
             }
             // 16 keys = 2 chunks of 16 B inside atom (ch/4); chunk index within the 128 B row = (ch%4)*2 + {0,1}
             uint8_t* atom = sP + (ch >> 2) * FA_TILE_BYTES + row * 128;
@@ -325,7 +330,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
         fence_proxy_async_smem();                   // every writer publishes its P stores to the async proxy ...
         __syncwarp();                               // ... before the warp's single arrive
         if (lane == 0) mbar_arrive(&p_full[buf]);
-        l_run = l_run * alpha + rs;
+        l_run = l_run * alpha + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
         m_run = m_new;
         if (g > 0) {
           consume_pv(g - 1, alpha_prev);            // block g-1 may be the last block of the previous tile
@@ -348,6 +353,11 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
     tmem_dealloc(tmem_base, 512);
   }
 }
+
+typedef void (*FaKernel)(const FaParams);
+static FaKernel fa_kernels[10] = {
+    attn_fa_kernel<false, 0>, attn_fa_kernel<false, 2>, attn_fa_kernel<false, 5>, attn_fa_kernel<false, 7>, attn_fa_kernel<false, 8>,
+    attn_fa_kernel<true, 0>,  attn_fa_kernel<true, 2>,  attn_fa_kernel<true, 5>,  attn_fa_kernel<true, 7>,  attn_fa_kernel<true, 8>};
 
 }  // namespace pn
 
@@ -420,16 +430,17 @@ extern "C" int pn_attention(const pn_attn_args* a, void* stream_v) {
   }
   static bool attr_set = false;
   if (!attr_set) {
-    PN_CHECK_CUDA(cudaFuncSetAttribute(attn_fa_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_TOTAL));
-    PN_CHECK_CUDA(cudaFuncSetAttribute(attn_fa_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_TOTAL));
+    for (int i = 0; i < 10; ++i)
+      PN_CHECK_CUDA(cudaFuncSetAttribute(fa_kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_TOTAL));
     attr_set = true;
   }
   const long long tiles = (long long)p.tiles_x * p.tiles_y * a->heads * a->V * a->F;
   PN_REQUIRE(tiles > 0 && tiles < (1ll << 31), "pn_attention: too many query tiles");
   p.total_tiles = (int)tiles;
   const int grid = tiles < sm_count() ? (int)tiles : sm_count();
-  if (p.kv_rows < p.kv_n) attn_fa_kernel<true><<<grid, FA_THREADS, FA_SMEM_TOTAL, reinterpret_cast<cudaStream_t>(stream_v)>>>(p);
-  else attn_fa_kernel<false><<<grid, FA_THREADS, FA_SMEM_TOTAL, reinterpret_cast<cudaStream_t>(stream_v)>>>(p);
+  const int nch = p.kv_n / 16;
+  const int slot = nch == 8 ? 4 : nch == 7 ? 3 : nch == 5 ? 2 : nch == 2 ? 1 : 0;
+  fa_kernels[(p.kv_rows < p.kv_n ? 5 : 0) + slot]<<<grid, FA_THREADS, FA_SMEM_TOTAL, reinterpret_cast<cudaStream_t>(stream_v)>>>(p);
   PN_CHECK_CUDA(cudaGetLastError());
   return PN_OK;
 }

@@ -27,7 +27,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle atom row
 // warp 0 TMA, warp 1 MMA, warps 2.. epilogue: 8 warps for the fp32/residual mode (168 registers each), 12 for the
 // ALU-heavy bf16 / GEGLU modes (the register file is granted per 4-warp group: 16 warps x 128 registers)
-constexpr int gemm_threads(int mode) { return mode == 0 ? 320 : 448; }
+constexpr int gemm_threads(int mode) { return (mode == 0 || mode == 3) ? 320 : 448; }
 
 struct GemmParams {
   CUtensorMap mapA;
@@ -54,7 +54,7 @@ struct GemmParams {
 template <int BN, int STAGES, int NCTA, int MODE>
 struct GemmSmem {
   static constexpr int NEPI = gemm_threads(MODE) / 32 - 2;
-  static constexpr int STAGE_WARP_BYTES = MODE == 0 ? 4096 : 2048;   // 32 rows x (128 | 64) B
+  static constexpr int STAGE_WARP_BYTES = (MODE == 0 || MODE == 3) ? 4096 : 2048;   // 32 rows x (128 | 64) B
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / NCTA) * BK * 2;   // a CTA pair splits the N tile: each CTA stages BN/2 weight rows
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -64,7 +64,8 @@ struct GemmSmem {
   static constexpr int TOTAL = STAGES * STAGE_BYTES + STAGING_BYTES + ROWMAP_BYTES + BAR_BYTES + 1024;
 };
 
-// MODE: 0 = fp32 store (+ up to two fp32 residuals), 1 = bf16 store, 2 = GEGLU (bf16 store of N/2 columns)
+// MODE: 0 = fp32 store (+ one fp32 residual), 1 = bf16 store, 2 = GEGLU (bf16 store of N/2 columns),
+//       3 = fp32 store + two fp32 residuals (kept apart so that mode 0 does not carry its registers)
 template <int BN, int STAGES, int NCTA, int MODE>
 __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using S = GemmSmem<BN, STAGES, NCTA, MODE>;
@@ -205,7 +206,8 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
     int* my_rowmap = rowmap + ew * 32;
     constexpr int NCH = BN / 32;
     constexpr int MYCH = (NCH + EG - 1) / EG;
-    constexpr int PRECH = MYCH < 3 ? MYCH : 3;   // chunks whose residual is prefetched at tile start (register budget)
+    constexpr int PRECH = MYCH < 2 ? MYCH : 2;   // chunks whose residual is prefetched at tile start (register budget:
+                                                 // a third chunk spills, and a spilled prefetch stalls on its own load)
     int acc = 0;
     uint32_t acc_phase = 0;
     // hand-back target: the leader CTA's tmem_empty barrier (remote arrive from the peer CTA of a pair)
@@ -235,7 +237,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
       const int n_base = tcol * BN;
       // ---- residual prefetch (fp32 output path): lane -> (row i*4 + lane/8, 16-byte column chunk lane%8)
       float4 rpre[PRECH][8];
-      const bool pre = (MODE == 0) && (p.residual != nullptr);
+      const bool pre = (MODE == 0 || MODE == 3) && (p.residual != nullptr);
       if (pre) {
 #pragma unroll
         for (int k = 0; k < PRECH; ++k) {
@@ -361,7 +363,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
             const int ch = lane & 7;
             const bool col_ok = n0 + ch * 4 < p.N;
             float4 r2[8];
-            if (p.residual2 != nullptr) {
+            if (MODE == 3) {
               // second addend: all eight loads are issued before the first store (out may alias a residual)
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
@@ -384,7 +386,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
                   else rr4 = *reinterpret_cast<const float4*>(p.residual + (long long)grow * p.ldr + n0 + ch * 4);
                   val.x += rr4.x; val.y += rr4.y; val.z += rr4.z; val.w += rr4.w;
                 }
-                if (p.residual2 != nullptr) { val.x += r2[i].x; val.y += r2[i].y; val.z += r2[i].z; val.w += r2[i].w; }
+                if (MODE == 3) { val.x += r2[i].x; val.y += r2[i].y; val.z += r2[i].z; val.w += r2[i].w; }
                 *reinterpret_cast<float4*>(out + (long long)grow * p.ldo + n0 + ch * 4) = val;
               }
             }
@@ -467,6 +469,7 @@ template <int BN, int STAGES, int NCTA>
 static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
   if (p.geglu) return launch_gemm_mode<BN, STAGES, NCTA, 2>(p, stream);
   if (p.out_bf16) return launch_gemm_mode<BN, STAGES, NCTA, 1>(p, stream);
+  if (p.residual2 != nullptr) return launch_gemm_mode<BN, STAGES, NCTA, 3>(p, stream);
   return launch_gemm_mode<BN, STAGES, NCTA, 0>(p, stream);
 }
 
@@ -547,7 +550,7 @@ extern "C" int pn_gemm(const pn_gemm_args* a, void* stream_v) {
   if (rc != PN_OK) return rc;
 
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
-  if (NCTA == 2) return BN == 256 ? launch_gemm<256, 5, 2>(p, stream) : launch_gemm<160, 6, 2>(p, stream);
+  if (NCTA == 2) return BN == 256 ? launch_gemm<256, 6, 2>(p, stream) : launch_gemm<160, 7, 2>(p, stream);
   switch (BN) {
     case 160: return launch_gemm<160, 5, 1>(p, stream);
     case 128: return launch_gemm<128, 6, 1>(p, stream);

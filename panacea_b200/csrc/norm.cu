@@ -18,35 +18,43 @@ constexpr int GN_GROUPS = 32;
 constexpr int GN_CHUNK = 64;  // pixels per partial-statistics block
 
 // ---------------------------------------------------------------- spatial GN: partial sums per pixel chunk
-// partial[f][chunk][g][2] = (sum, sumsq) over the chunk's pixels x group channels (fp32, <= 64*cpg terms each)
+// partial[f][chunk][g][2] = (sum, sumsq) over the chunk's pixels x group channels (fp32, <= 64*cpg terms each).
+// Thread layout: (pixel lane, float4 column). With C = 320 a block of 256 threads runs 3 pixel lanes x 80 columns,
+// so (almost) every thread streams; per-lane column sums meet in shared memory and are reduced in a fixed order
+// (bit-reproducible, no atomics).
 __global__ void __launch_bounds__(256) gn_partial_kernel(const float* __restrict__ x, float* __restrict__ partial,
-                                                         int P, int C, int nchunks) {
-  extern __shared__ float colacc[];   // [2][C]: per-channel sum / sum of squares of this pixel chunk
+                                                         int P, int C, int nchunks, int PL) {
+  extern __shared__ float colacc[];   // [PL][2][C]
   const int f = blockIdx.y, chunk = blockIdx.x;
   const int cpg = C / GN_GROUPS;
   const int p0 = chunk * GN_CHUNK;
   const int p1 = min(P, p0 + GN_CHUNK);
   const int c4n = C / 4;
   const float* base = x + ((size_t)f * P) * C;
-  for (int c4 = threadIdx.x; c4 < c4n; c4 += blockDim.x) {
-    float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int p = p0; p < p1; ++p) {
-      const float4 v = *reinterpret_cast<const float4*>(base + (size_t)p * C + c4 * 4);
-      s[0] += v.x; q[0] += v.x * v.x;
-      s[1] += v.y; q[1] += v.y * v.y;
-      s[2] += v.z; q[2] += v.z * v.z;
-      s[3] += v.w; q[3] += v.w * v.w;
+  const int cols = c4n < 256 ? c4n : 256;
+  const int pl = threadIdx.x / cols;
+  if (pl < PL) {
+    for (int c4 = threadIdx.x - pl * cols; c4 < c4n; c4 += cols) {
+      float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int p = p0 + pl; p < p1; p += PL) {
+        const float4 v = *reinterpret_cast<const float4*>(base + (size_t)p * C + c4 * 4);
+        s[0] += v.x; q[0] += v.x * v.x;
+        s[1] += v.y; q[1] += v.y * v.y;
+        s[2] += v.z; q[2] += v.z * v.z;
+        s[3] += v.w; q[3] += v.w * v.w;
+      }
+      *reinterpret_cast<float4*>(colacc + (size_t)pl * 2 * C + c4 * 4) = make_float4(s[0], s[1], s[2], s[3]);
+      *reinterpret_cast<float4*>(colacc + (size_t)pl * 2 * C + C + c4 * 4) = make_float4(q[0], q[1], q[2], q[3]);
     }
-    *reinterpret_cast<float4*>(colacc + c4 * 4) = make_float4(s[0], s[1], s[2], s[3]);
-    *reinterpret_cast<float4*>(colacc + C + c4 * 4) = make_float4(q[0], q[1], q[2], q[3]);
   }
   __syncthreads();
-  // fixed-order reduction over the group's channels: bit-reproducible (no atomics)
   if (threadIdx.x < GN_GROUPS * 2) {
     const int g = threadIdx.x >> 1, which = threadIdx.x & 1;
-    const float* src = colacc + which * C + g * cpg;
     float acc = 0.f;
-    for (int j = 0; j < cpg; ++j) acc += src[j];
+    for (int l = 0; l < PL; ++l) {
+      const float* src = colacc + (size_t)l * 2 * C + which * C + g * cpg;
+      for (int j = 0; j < cpg; ++j) acc += src[j];
+    }
     partial[((size_t)f * nchunks + chunk) * GN_GROUPS * 2 + threadIdx.x] = acc;
   }
 }
@@ -56,15 +64,22 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, const floa
                                    const float* __restrict__ beta, float* __restrict__ scale,
                                    float* __restrict__ shift, int P, int C, int nchunks, float eps) {
   __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
+  __shared__ double s_part[4][GN_GROUPS * 2];
   const int f = blockIdx.x;
   const int cpg = C / GN_GROUPS;
+  {
+    // 256 threads: (chunk quarter, group, sum|sumsq); double-precision combine in a fixed order
+    const int slot = threadIdx.x & 63, quarter = threadIdx.x >> 6;
+    double acc = 0.0;
+    const float* pp = partial + (size_t)f * nchunks * GN_GROUPS * 2 + slot;
+    for (int k = quarter; k < nchunks; k += 4) acc += (double)pp[(size_t)k * GN_GROUPS * 2];
+    s_part[quarter][slot] = acc;
+  }
+  __syncthreads();
   if (threadIdx.x < GN_GROUPS) {
-    double s = 0.0, q = 0.0;
-    const float* pp = partial + (size_t)f * nchunks * GN_GROUPS * 2 + threadIdx.x * 2;
-    for (int k = 0; k < nchunks; ++k) {
-      s += (double)pp[(size_t)k * GN_GROUPS * 2];
-      q += (double)pp[(size_t)k * GN_GROUPS * 2 + 1];
-    }
+    const int g = threadIdx.x;
+    const double s = (s_part[0][2 * g] + s_part[1][2 * g]) + (s_part[2][2 * g] + s_part[3][2 * g]);
+    const double q = (s_part[0][2 * g + 1] + s_part[1][2 * g + 1]) + (s_part[2][2 * g + 1] + s_part[3][2 * g + 1]);
     const double n = (double)P * cpg;
     const double mean = s / n;
     double var = q / n - mean * mean;
@@ -81,42 +96,52 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, const floa
   }
 }
 
-// y = act(x*scale[f,c] + shift[f,c]) -> bf16 ; optional raw bf16 copy of x (input of the 1x1 skip conv)
+// y = act(x*scale[f,c] + shift[f,c]) -> bf16 ; optional raw bf16 copy of x (input of the 1x1 skip conv).
+// Thread layout: (pixel lane, 8-channel column) fixed per thread, so scale/shift live in registers and the loop has
+// no integer division; a block covers GN_APPLY_PIX pixels of one frame.
+constexpr int GN_APPLY_PIX = 64;
 __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                                                        const float* __restrict__ shift,
                                                        __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ raw,
                                                        int P, int C, int act_silu) {
-  extern __shared__ float sm[];
-  float* s_scale = sm;
-  float* s_shift = sm + C;
   const int f = blockIdx.y;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    s_scale[c] = scale[(size_t)f * C + c];
-    s_shift[c] = shift[(size_t)f * C + c];
-  }
-  __syncthreads();
   const int c8n = C / 8;
-  const size_t total = (size_t)P * c8n;
+  const int cols = c8n < 256 ? c8n : 256;
+  const int PL = 256 / cols;
+  const int pl = threadIdx.x / cols;
+  if (pl >= PL) return;
+  const int p0 = blockIdx.x * GN_APPLY_PIX;
+  const int p1 = min(P, p0 + GN_APPLY_PIX);
   const float* xb = x + (size_t)f * P * C;
   __nv_bfloat16* yb = y + (size_t)f * P * C;
   __nv_bfloat16* rb = raw ? raw + (size_t)f * P * C : nullptr;
-  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-    const int c8 = (int)(e % c8n);
-    const size_t off = (e / c8n) * C + (size_t)c8 * 8;
-    const float4 a = *reinterpret_cast<const float4*>(xb + off);
-    const float4 b = *reinterpret_cast<const float4*>(xb + off + 4);
-    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    if (rb) {
-      *reinterpret_cast<uint4*>(rb + off) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+  for (int c8 = threadIdx.x - pl * cols; c8 < c8n; c8 += cols) {
+    float sc[8], sh[8];
+    {
+      const float4 a = *reinterpret_cast<const float4*>(scale + (size_t)f * C + c8 * 8);
+      const float4 b = *reinterpret_cast<const float4*>(scale + (size_t)f * C + c8 * 8 + 4);
+      const float4 c = *reinterpret_cast<const float4*>(shift + (size_t)f * C + c8 * 8);
+      const float4 d = *reinterpret_cast<const float4*>(shift + (size_t)f * C + c8 * 8 + 4);
+      sc[0] = a.x; sc[1] = a.y; sc[2] = a.z; sc[3] = a.w; sc[4] = b.x; sc[5] = b.y; sc[6] = b.z; sc[7] = b.w;
+      sh[0] = c.x; sh[1] = c.y; sh[2] = c.z; sh[3] = c.w; sh[4] = d.x; sh[5] = d.y; sh[6] = d.z; sh[7] = d.w;
+    }
+    for (int p = p0 + pl; p < p1; p += PL) {
+      const size_t off = (size_t)p * C + (size_t)c8 * 8;
+      const float4 a = *reinterpret_cast<const float4*>(xb + off);
+      const float4 b = *reinterpret_cast<const float4*>(xb + off + 4);
+      float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      if (rb) {
+        *reinterpret_cast<uint4*>(rb + off) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                          pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float t = v[j] * sc[j] + sh[j];
+        v[j] = act_silu ? silu(t) : t;
+      }
+      *reinterpret_cast<uint4*>(yb + off) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
                                                         pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float t = v[j] * s_scale[c8 * 8 + j] + s_shift[c8 * 8 + j];
-      v[j] = act_silu ? silu(t) : t;
-    }
-    *reinterpret_cast<uint4*>(yb + off) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
-                                                      pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
   }
 }
 
@@ -239,18 +264,15 @@ extern "C" int pn_groupnorm_silu(const float* x, const float* gamma, const float
   float* partial = workspace;
   float* scale = workspace + (size_t)F * nchunks * GN_GROUPS * 2;
   float* shift = scale + (size_t)F * C;
-  gn_partial_kernel<<<dim3(nchunks, F), 256, 2 * C * sizeof(float), st>>>(x, partial, P, C, nchunks);
+  const int c4n = C / 4;
+  const int PL = c4n < 256 ? 256 / c4n : 1;
+  gn_partial_kernel<<<dim3(nchunks, F), 256, (size_t)PL * 2 * C * sizeof(float), st>>>(x, partial, P, C, nchunks, PL);
   PN_CHECK_CUDA(cudaGetLastError());
   gn_finalize_kernel<<<F, 256, 0, st>>>(partial, gamma, beta, scale, shift, P, C, nchunks, eps);
   PN_CHECK_CUDA(cudaGetLastError());
-  const size_t total = (size_t)P * (C / 8);
-  int gx = (int)((total + 255) / 256);
-  const int cap = 8 * sm_count() / (F > 0 ? 1 : 1);
-  if (gx > cap) gx = cap;
-  if (gx < 1) gx = 1;
-  gn_apply_kernel<<<dim3(gx, F), 256, 2 * C * sizeof(float), st>>>(
-      x, scale, shift, reinterpret_cast<__nv_bfloat16*>(y_bf16), reinterpret_cast<__nv_bfloat16*>(raw_bf16), P, C,
-      act_silu);
+  const int gx = (P + GN_APPLY_PIX - 1) / GN_APPLY_PIX;
+  gn_apply_kernel<<<dim3(gx, F), 256, 0, st>>>(x, scale, shift, reinterpret_cast<__nv_bfloat16*>(y_bf16),
+                                                reinterpret_cast<__nv_bfloat16*>(raw_bf16), P, C, act_silu);
   PN_CHECK_CUDA(cudaGetLastError());
   return PN_OK;
 }
