@@ -269,6 +269,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float rcp_approx(float x) {   // one MUFU.RCP, no IEEE fix-up subroutine
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 // 1024-byte aligned start of the dynamic shared-memory window WITHOUT leaving the shared address space (an integer
 // round trip through uintptr_t makes the compiler fall back to generic LD/ST instead of LDS/STS)
 __device__ __forceinline__ uint8_t* smem_align1024(uint8_t* base) {
@@ -283,16 +288,16 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 // ~30-instruction libdevice erff; used where the result is rounded to bf16 anyway (GEGLU epilogue).
 __device__ __forceinline__ float erf_fast(float x) {
   const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
   poly *= t;
-  const float r = 1.0f - poly * __expf(-ax * ax);
+  const float r = 1.0f - poly * ex2_approx(-1.4426950408889634f * ax * ax);
   return copysignf(r, x);
 }
 __device__ __forceinline__ float gelu_erf_fast(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu(float x) { return x * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
 
 }  // namespace pn
