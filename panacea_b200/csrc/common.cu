@@ -38,6 +38,48 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+static std::mutex g_tmap32_mu;
+struct Tmap32Key {
+  const void* ptr; uint64_t cols, rows, ld; uint32_t box_rows, pad;
+  bool operator==(const Tmap32Key& o) const { return std::memcmp(this, &o, sizeof(Tmap32Key)) == 0; }
+};
+struct Tmap32Hash {
+  size_t operator()(const Tmap32Key& k) const {
+    const unsigned char* w = reinterpret_cast<const unsigned char*>(&k);
+    size_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(Tmap32Key); ++i) h = (h ^ w[i]) * 1099511628211ull;
+    return h;
+  }
+};
+static std::unordered_map<Tmap32Key, CUtensorMap, Tmap32Hash> g_tmap32_cache;
+
+int cached_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_rows) {
+  Tmap32Key key;
+  std::memset(&key, 0, sizeof(key));
+  key.ptr = base; key.cols = cols; key.rows = rows; key.ld = ld_elems; key.box_rows = box_rows;
+  {
+    std::lock_guard<std::mutex> lk(g_tmap32_mu);
+    auto it = g_tmap32_cache.find(key);
+    if (it != g_tmap32_cache.end()) { *out = it->second; return PN_OK; }
+  }
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return fail(PN_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {ld_elems * 4};
+  cuuint32_t bdim[2] = {32u, box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, bdim, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(PN_ERR_CUDA, "cuTensorMapEncodeTiled(fp32) failed (%d): cols=%llu rows=%llu ld=%llu", (int)r,
+                (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)ld_elems);
+  std::lock_guard<std::mutex> lk(g_tmap32_mu);
+  if (g_tmap32_cache.size() > 65536) g_tmap32_cache.clear();
+  g_tmap32_cache.emplace(key, *out);
+  return PN_OK;
+}
+
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_elems, const uint32_t* box, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();

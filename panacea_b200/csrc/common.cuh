@@ -34,6 +34,9 @@ int fail(int code, const char* fmt, ...);
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_elems, const uint32_t* box, int swizzle_bytes);
 
+// fp32 2-D [rows, ld] map with a {32 floats, box_rows} box, 128B swizzle (streaming GEMM epilogue)
+int cached_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_rows);
+
 int cached_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_elems, const uint32_t* box, int swizzle_bytes);
 

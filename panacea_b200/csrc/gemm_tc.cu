@@ -27,11 +27,14 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle atom row
 // warp 0 TMA, warp 1 MMA, warps 2.. epilogue: 8 warps for the fp32/residual mode (168 registers each), 12 for the
 // ALU-heavy bf16 / GEGLU modes (the register file is granted per 4-warp group: 16 warps x 128 registers)
-constexpr int gemm_threads(int mode) { return (mode == 0 || mode == 3) ? 320 : 448; }
+constexpr int gemm_threads(int mode) { return (mode == 0 || mode == 3) ? 320 : mode == 4 ? 352 : 448; }
 
 struct GemmParams {
   CUtensorMap mapA;
   CUtensorMap mapB;
+  CUtensorMap mapOut;          // MODE 4 only: fp32 output / residual, box {32 floats, 128 rows}
+  CUtensorMap mapRes;
+  int has_res;
   // geometry of the A tensor / output rows
   int NB, H, W;
   int tw, th, tn;             // tile box extents, tw*th*tn == 128
@@ -53,19 +56,24 @@ struct GemmParams {
 
 template <int BN, int STAGES, int NCTA, int MODE>
 struct GemmSmem {
-  static constexpr int NEPI = gemm_threads(MODE) / 32 - 2;
+  static constexpr int NEPI = MODE == 4 ? 8 : gemm_threads(MODE) / 32 - 2;
   static constexpr int STAGE_WARP_BYTES = (MODE == 0 || MODE == 3) ? 4096 : 2048;   // 32 rows x (128 | 64) B
+  static constexpr int RCHUNK_BYTES = 128 * 128;                                      // MODE 4: 128 rows x 32 fp32
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / NCTA) * BK * 2;   // a CTA pair splits the N tile: each CTA stages BN/2 weight rows
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGING_BYTES = NEPI * STAGE_WARP_BYTES;
-  static constexpr int ROWMAP_BYTES = NEPI * 32 * 4;
-  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+  static constexpr int STAGING_BYTES = MODE == 4 ? (BN / 32) * RCHUNK_BYTES : NEPI * STAGE_WARP_BYTES;
+  static constexpr int ROWMAP_BYTES = MODE == 4 ? 0 : NEPI * 32 * 4;
+  static constexpr int BAR_BYTES = (2 * STAGES + 4 + 2 * (BN / 32)) * 8 + 16;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + STAGING_BYTES + ROWMAP_BYTES + BAR_BYTES + 1024;
 };
 
 // MODE: 0 = fp32 store (+ one fp32 residual), 1 = bf16 store, 2 = GEGLU (bf16 store of N/2 columns),
-//       3 = fp32 store + two fp32 residuals (kept apart so that mode 0 does not carry its registers)
+//       3 = fp32 store + two fp32 residuals (kept apart so that mode 0 does not carry its registers),
+//       4 = streaming fp32 epilogue for tiles whose 128 rows are consecutive output rows: the fp32 residual tile is
+//           TMA-loaded into a swizzled shared-memory tile ahead of time, the epilogue warps update it in place
+//           (thread == row, conflict-free), and a dedicated warp TMA-stores it — no global LD/ST instruction and no
+//           register prefetch in the epilogue warps. Used for the HBM-bound K<=1280 linears and the temporal conv.
 template <int BN, int STAGES, int NCTA, int MODE>
 __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using S = GemmSmem<BN, STAGES, NCTA, MODE>;
@@ -80,7 +88,9 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* r_full = tmem_empty + 2;          // [BN/32]  MODE 4: tile chunk holds the residual / is free for the epilogue
+  uint64_t* c_ready = r_full + BN / 32;       // [BN/32]  MODE 4: chunk updated by its 4 epilogue warps -> store it
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(c_ready + BN / 32);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -108,6 +118,14 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], NEPI * NCTA);  // one arrive per epilogue warp (of both CTAs of a pair)
+    }
+    if (MODE == 4) {
+      tma_prefetch_desc(&p.mapOut);
+      if (p.has_res) tma_prefetch_desc(&p.mapRes);
+      for (int i = 0; i < BN / 32; ++i) {
+        mbar_init(&r_full[i], 1);
+        mbar_init(&c_ready[i], 4);
+      }
     }
     fence_barrier_init();
   }
@@ -193,6 +211,130 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+    }
+  } else if (MODE == 4 && warp == 10) {
+    // ===================== MODE 4: residual-load / output-store warp =====================
+    if (lane == 0) {
+      constexpr int NCH = BN / 32;
+      bool first = true;
+      int it = 0;
+      for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
+        const int tcol = tile % p.tiles_col;
+        int tm = (tile / p.tiles_col) * NCTA + (int)cta_rank;
+        const int twi = tm % p.tiles_w; tm /= p.tiles_w;
+        const int thi = tm % p.tiles_h; tm /= p.tiles_h;
+        const int m0 = (tm * p.H + thi) * p.W + twi * p.tw;      // th == tn == 1: 128 consecutive output rows
+        const int n0 = tcol * BN;
+        if (first) {
+          for (int c = 0; c < NCH; ++c) {
+            if (p.has_res) {
+              mbar_arrive_expect_tx(&r_full[c], S::RCHUNK_BYTES);
+              tma_load_2d(staging + c * S::RCHUNK_BYTES, &p.mapRes, &r_full[c], n0 + c * 32, m0);
+            } else {
+              mbar_arrive(&r_full[c]);
+            }
+          }
+          first = false;
+        }
+        const int ntile = tile + num_units;
+        int nm0 = 0, nn0 = 0;
+        if (ntile < num_tiles) {
+          int t2 = (ntile / p.tiles_col) * NCTA + (int)cta_rank;
+          const int w2 = t2 % p.tiles_w; t2 /= p.tiles_w;
+          const int h2 = t2 % p.tiles_h; t2 /= p.tiles_h;
+          nm0 = (t2 * p.H + h2) * p.W + w2 * p.tw;
+          nn0 = (ntile % p.tiles_col) * BN;
+        }
+        for (int c = 0; c < NCH; ++c) {
+          mbar_wait(&c_ready[c], (uint32_t)(it & 1));
+          tma_store_2d(&p.mapOut, staging + c * S::RCHUNK_BYTES, n0 + c * 32, m0);
+          tma_store_commit();
+          tma_store_wait_read();                       // the chunk has left shared memory: reuse it for the next tile
+          if (ntile < num_tiles) {
+            if (p.has_res) {
+              mbar_arrive_expect_tx(&r_full[c], S::RCHUNK_BYTES);
+              tma_load_2d(staging + c * S::RCHUNK_BYTES, &p.mapRes, &r_full[c], nn0 + c * 32, nm0);
+            } else {
+              mbar_arrive(&r_full[c]);
+            }
+          }
+        }
+      }
+      tma_store_wait_all();
+    }
+  } else if (MODE == 4) {
+    // ===================== MODE 4: epilogue warps 2..9, thread == tile row =====================
+    const int ew = warp - 2;
+    const int lane_grp = warp & 3;
+    const int half = ew >> 2;
+    const int r = lane_grp * 32 + lane;
+    constexpr int NCH = BN / 32;
+    constexpr int MYCH = (NCH + 1) / 2;
+    const uint32_t te_addr0 = (NCTA == 2) ? mapa_shared(smem_u32(&tmem_empty[0]), 0) : smem_u32(&tmem_empty[0]);
+    int acc = 0, it = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
+      const int tcol = tile % p.tiles_col;
+      int tm = (tile / p.tiles_col) * NCTA + (int)cta_rank;
+      const int twi = tm % p.tiles_w; tm /= p.tiles_w;
+      const int thi = tm % p.tiles_h; tm /= p.tiles_h;
+      const long long grow = (long long)(tm * p.H + thi) * p.W + twi * p.tw + r;
+      const int n_base = tcol * BN;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (uint32_t(lane_grp * 32) << 16) + acc * BN;
+#pragma unroll
+      for (int k = 0; k < MYCH; ++k) {
+        const int c = half + 2 * k;
+        if (c < NCH) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_row + c * 32, v);
+          tmem_ld_wait();
+          if (c + 2 >= NCH) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (NCTA == 2) mbar_arrive_cluster(te_addr0 + acc * 8);
+              else mbar_arrive(&tmem_empty[acc]);
+            }
+          }
+          const int n0 = n_base + c * 32;
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+              f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+            }
+          }
+          if (p.rowvec != nullptr) {
+            const float* rv = p.rowvec + (long long)((grow / p.rows_per_group) % p.n_groups) * p.ldv;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(rv + n0 + j));
+              f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+            }
+          }
+          mbar_wait(&r_full[c], (uint32_t)(it & 1));
+          uint8_t* rowp = staging + c * S::RCHUNK_BYTES + r * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4* q = reinterpret_cast<float4*>(rowp + ((j ^ (r & 7)) << 4));
+            float4 o = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            if (p.has_res) {
+              const float4 a = *q;
+              o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+            }
+            *q = o;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&c_ready[c]);
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ===================== epilogue warps: TMEM lane quarter = warp & 3, chunk residue = (warp - 2) / 4 ==========
@@ -411,6 +553,15 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+static int gemm_stream_kmax() {
+  static int kmax = -1;
+  if (kmax < 0) {
+    const char* e = getenv("PN_GEMM_STREAM_KMAX");     // 0 disables the streaming epilogue
+    kmax = e ? atoi(e) : 1920;
+  }
+  return kmax;
+}
+
 static int gemm_mode_override() {
   static int mode = -1;
   if (mode < 0) {
@@ -535,6 +686,23 @@ extern "C" int pn_gemm(const pn_gemm_args* a, void* stream_v) {
   else if (a->N >= 128) BN = 128;
   else if (a->N > 32) BN = 64;
   else BN = 32;
+  // Streaming epilogue (MODE 4): fp32 output whose tile rows are consecutive output rows, short K loop (HBM-bound).
+  const long long k_total = (long long)a->taps_h * a->taps_w * a->C;
+  const bool rows_contig = (tw == 128 && th == 1 && tn == 1) && ((H == 1 && NB == 1) || (W % 128 == 0));
+  bool stream_mode = !a->out_bf16 && !a->geglu && a->residual2 == nullptr && rows_contig && k_total <= gemm_stream_kmax() &&
+                     (a->N % 160 == 0 || a->N % 128 == 0) && a->ldo % 4 == 0 && (a->residual == nullptr || a->ldr % 4 == 0);
+  if (stream_mode) {
+    BN = (a->N % 160 == 0) ? 160 : 128;
+    NCTA = (force == 2 || (force == 0 && tiles_m_1 * (a->N / BN) >= 2 * sm_count())) ? 2 : 1;
+    const uint64_t rows_total = (uint64_t)NB * H * W;
+    int rc2 = cached_tmap_f32_2d(&p.mapOut, a->out, (uint64_t)a->N, rows_total, (uint64_t)a->ldo, 128u);
+    if (rc2 != PN_OK) return rc2;
+    p.has_res = a->residual != nullptr ? 1 : 0;
+    if (p.has_res) {
+      rc2 = cached_tmap_f32_2d(&p.mapRes, a->residual, (uint64_t)a->N, rows_total, (uint64_t)a->ldr, 128u);
+      if (rc2 != PN_OK) return rc2;
+    }
+  }
   p.tiles_col = (a->N + BN - 1) / BN;
 
   const uint64_t dimsA[4] = {(uint64_t)a->C, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
@@ -550,6 +718,10 @@ extern "C" int pn_gemm(const pn_gemm_args* a, void* stream_v) {
   if (rc != PN_OK) return rc;
 
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  if (stream_mode) {
+    if (NCTA == 2) return BN == 160 ? launch_gemm_mode<160, 5, 2, 4>(p, stream) : launch_gemm_mode<128, 6, 2, 4>(p, stream);
+    return BN == 160 ? launch_gemm_mode<160, 4, 1, 4>(p, stream) : launch_gemm_mode<128, 5, 1, 4>(p, stream);
+  }
   if (NCTA == 2) return BN == 256 ? launch_gemm<256, 6, 2>(p, stream) : launch_gemm<160, 7, 2>(p, stream);
   switch (BN) {
     case 160: return launch_gemm<160, 5, 1>(p, stream);

@@ -108,3 +108,19 @@ def test_temporal_conv(ops, b, T, P, C):
     xin = x.float().permute(0, 2, 3, 1).reshape(b * P, C, T)
     ref = F.conv1d(xin, w.float(), padding=1).reshape(b, P, C, T).permute(0, 3, 1, 2) + res
     _check(out.reshape(b, T, P, C), ref, name="temporal conv")
+
+
+@pytest.mark.parametrize("M,N,K,G", [(2048, 320, 320, 8), (1536, 640, 64, 3), (640, 128, 128, 5)])
+def test_gemm_fp32_rowvec_residual_streaming_epilogue(ops, M, N, K, G):
+    """fp32 output + per-row-group vector (time-emb / pos-emb) + in-place residual: the TMA streaming epilogue."""
+    a = _rand((M, K), 30); w = _rand((N, K), 31, K ** -0.5)
+    bias = _rand((N,), 32, dtype=torch.float32)
+    rv_full = _rand((G, N + 64), 33, dtype=torch.float32)
+    rv = rv_full[:, 32:32 + N]                               # strided rows (slice of a wider matrix)
+    res = _rand((M, N), 34, dtype=torch.float32)
+    rpg = M // (2 * G)
+    grp = (torch.arange(M, device="cuda") // rpg) % G
+    ref = a.float() @ w.float().t() + bias + rv[grp] + res
+    out = ops.gemm(a, w, bias=bias, rowvec=rv, rows_per_group=rpg, n_groups=G, residual=res, out=res)
+    torch.cuda.synchronize()
+    _check(out, ref, name="fp32 rowvec+residual")
