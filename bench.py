@@ -228,6 +228,8 @@ def profile_dominant_kernel(pipe, x_in, t_dev, cc):
         recs.append((2.0 * rows * w.shape[0] * w.shape[1], s, e))
         return out
 
+    eng.eps(x_in, cc["concat"].float().contiguous(), t_dev)      # untimed eager pass (module load, allocator warm-up)
+    torch.cuda.synchronize()
     ops.gemm = timed
     try:
         eng.eps(x_in, cc["concat"].float().contiguous(), t_dev)
