@@ -27,7 +27,8 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle atom row
 // warp 0 TMA, warp 1 MMA, warps 2.. epilogue: 8 warps for the fp32/residual mode (168 registers each), 12 for the
 // ALU-heavy bf16 / GEGLU modes (the register file is granted per 4-warp group: 16 warps x 128 registers)
-constexpr int gemm_threads(int mode) { return (mode == 0 || mode == 3) ? 320 : mode == 4 ? 352 : 448; }
+constexpr bool gemm_streaming(int mode) { return mode == 4 || mode == 5; }
+constexpr int gemm_threads(int mode) { return (mode == 0 || mode == 3) ? 320 : gemm_streaming(mode) ? 352 : 448; }
 
 struct GemmParams {
   CUtensorMap mapA;
@@ -56,14 +57,14 @@ struct GemmParams {
 
 template <int BN, int STAGES, int NCTA, int MODE>
 struct GemmSmem {
-  static constexpr int NEPI = MODE == 4 ? 8 : gemm_threads(MODE) / 32 - 2;
+  static constexpr int NEPI = gemm_streaming(MODE) ? 8 : gemm_threads(MODE) / 32 - 2;
   static constexpr int STAGE_WARP_BYTES = (MODE == 0 || MODE == 3) ? 4096 : 2048;   // 32 rows x (128 | 64) B
-  static constexpr int RCHUNK_BYTES = 128 * 128;                                      // MODE 4: 128 rows x 32 fp32
+  static constexpr int RCHUNK_BYTES = MODE == 5 ? 128 * 64 : 128 * 128;              // 128 rows x 32 (bf16 | fp32)
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / NCTA) * BK * 2;   // a CTA pair splits the N tile: each CTA stages BN/2 weight rows
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGING_BYTES = MODE == 4 ? (BN / 32) * RCHUNK_BYTES : NEPI * STAGE_WARP_BYTES;
-  static constexpr int ROWMAP_BYTES = MODE == 4 ? 0 : NEPI * 32 * 4;
+  static constexpr int STAGING_BYTES = gemm_streaming(MODE) ? (BN / 32) * RCHUNK_BYTES : NEPI * STAGE_WARP_BYTES;
+  static constexpr int ROWMAP_BYTES = gemm_streaming(MODE) ? 0 : NEPI * 32 * 4;
   static constexpr int BAR_BYTES = (2 * STAGES + 4 + 2 * (BN / 32)) * 8 + 16;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + STAGING_BYTES + ROWMAP_BYTES + BAR_BYTES + 1024;
 };
@@ -74,6 +75,7 @@ struct GemmSmem {
 //           TMA-loaded into a swizzled shared-memory tile ahead of time, the epilogue warps update it in place
 //           (thread == row, conflict-free), and a dedicated warp TMA-stores it — no global LD/ST instruction and no
 //           register prefetch in the epilogue warps. Used for the HBM-bound K<=1280 linears and the temporal conv.
+//       5 = the same streaming epilogue with a bf16 store and no residual (q/k/v and query projections).
 template <int BN, int STAGES, int NCTA, int MODE>
 __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using S = GemmSmem<BN, STAGES, NCTA, MODE>;
@@ -119,7 +121,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], NEPI * NCTA);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
-    if (MODE == 4) {
+    if (gemm_streaming(MODE)) {
       tma_prefetch_desc(&p.mapOut);
       if (p.has_res) tma_prefetch_desc(&p.mapRes);
       for (int i = 0; i < BN / 32; ++i) {
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (MODE == 4 && warp == 10) {
+  } else if (gemm_streaming(MODE) && warp == 10) {
     // ===================== MODE 4: residual-load / output-store warp =====================
     if (lane == 0) {
       constexpr int NCH = BN / 32;
@@ -262,8 +264,8 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
       }
       tma_store_wait_all();
     }
-  } else if (MODE == 4) {
-    // ===================== MODE 4: epilogue warps 2..9, thread == tile row =====================
+  } else if (gemm_streaming(MODE)) {
+    // ===================== MODE 4/5: epilogue warps 2..9, thread == tile row =====================
     const int ew = warp - 2;
     const int lane_grp = warp & 3;
     const int half = ew >> 2;
@@ -318,16 +320,27 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
             }
           }
           mbar_wait(&r_full[c], (uint32_t)(it & 1));
-          uint8_t* rowp = staging + c * S::RCHUNK_BYTES + r * 128;
+          if (MODE == 5) {
+            // 32 bf16 = 64 B per row; TMA SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3
+            uint8_t* rowp = staging + c * S::RCHUNK_BYTES + r * 64;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4* q = reinterpret_cast<float4*>(rowp + ((j ^ (r & 7)) << 4));
-            float4 o = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-            if (p.has_res) {
-              const float4 a = *q;
-              o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+            for (int j = 0; j < 4; ++j) {
+              *reinterpret_cast<uint4*>(rowp + ((j ^ ((r >> 1) & 3)) << 4)) =
+                  make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                             pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
             }
-            *q = o;
+          } else {
+            uint8_t* rowp = staging + c * S::RCHUNK_BYTES + r * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4* q = reinterpret_cast<float4*>(rowp + ((j ^ (r & 7)) << 4));
+              float4 o = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+              if (p.has_res) {
+                const float4 a = *q;
+                o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+              }
+              *q = o;
+            }
           }
           fence_proxy_async_smem();
           __syncwarp();
@@ -689,13 +702,23 @@ extern "C" int pn_gemm(const pn_gemm_args* a, void* stream_v) {
   // Streaming epilogue (MODE 4): fp32 output whose tile rows are consecutive output rows, short K loop (HBM-bound).
   const long long k_total = (long long)a->taps_h * a->taps_w * a->C;
   const bool rows_contig = (tw == 128 && th == 1 && tn == 1) && ((H == 1 && NB == 1) || (W % 128 == 0));
-  bool stream_mode = !a->out_bf16 && !a->geglu && a->residual2 == nullptr && rows_contig && k_total <= gemm_stream_kmax() &&
-                     (a->N % 160 == 0 || a->N % 128 == 0) && a->ldo % 4 == 0 && (a->residual == nullptr || a->ldr % 4 == 0);
+  const bool stream_bf16 = a->out_bf16 && !a->geglu && a->residual == nullptr && a->ldo % 8 == 0;
+  const bool stream_f32 = !a->out_bf16 && !a->geglu && a->ldo % 4 == 0 && (a->residual == nullptr || a->ldr % 4 == 0);
+  bool stream_mode = (stream_bf16 || stream_f32) && a->residual2 == nullptr && rows_contig && k_total <= gemm_stream_kmax() &&
+                     (a->N % 160 == 0 || a->N % 128 == 0);
   if (stream_mode) {
     BN = (a->N % 160 == 0) ? 160 : 128;
     NCTA = (force == 2 || (force == 0 && tiles_m_1 * (a->N / BN) >= 2 * sm_count())) ? 2 : 1;
     const uint64_t rows_total = (uint64_t)NB * H * W;
-    int rc2 = cached_tmap_f32_2d(&p.mapOut, a->out, (uint64_t)a->N, rows_total, (uint64_t)a->ldo, 128u);
+    int rc2;
+    if (stream_bf16) {
+      const uint64_t dimsO[2] = {(uint64_t)a->N, rows_total};
+      const uint64_t strO[1] = {(uint64_t)a->ldo};
+      const uint32_t boxO[2] = {32u, 128u};
+      rc2 = cached_tmap_bf16(&p.mapOut, a->out, 2, dimsO, strO, boxO, 64);
+    } else {
+      rc2 = cached_tmap_f32_2d(&p.mapOut, a->out, (uint64_t)a->N, rows_total, (uint64_t)a->ldo, 128u);
+    }
     if (rc2 != PN_OK) return rc2;
     p.has_res = a->residual != nullptr ? 1 : 0;
     if (p.has_res) {
@@ -718,6 +741,10 @@ extern "C" int pn_gemm(const pn_gemm_args* a, void* stream_v) {
   if (rc != PN_OK) return rc;
 
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  if (stream_mode && a->out_bf16) {
+    if (NCTA == 2) return BN == 160 ? launch_gemm_mode<160, 6, 2, 5>(p, stream) : launch_gemm_mode<128, 7, 2, 5>(p, stream);
+    return BN == 160 ? launch_gemm_mode<160, 5, 1, 5>(p, stream) : launch_gemm_mode<128, 6, 1, 5>(p, stream);
+  }
   if (stream_mode) {
     if (NCTA == 2) return BN == 160 ? launch_gemm_mode<160, 5, 2, 4>(p, stream) : launch_gemm_mode<128, 6, 2, 4>(p, stream);
     return BN == 160 ? launch_gemm_mode<160, 4, 1, 4>(p, stream) : launch_gemm_mode<128, 5, 1, 4>(p, stream);

@@ -146,46 +146,56 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
 }
 
 // ---------------------------------------------------------------- pixel-wise temporal GN (+SiLU) -> bf16
-// x: fp32 [b, T, P, C]; one warp per (b, p); lane = group (32 groups); statistics over T x cpg values.
-__global__ void __launch_bounds__(256) gn_pixel_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+// x: fp32 [b, T, P, C]. One block per (b, p); thread (t, g) = (warp, lane) owns the cpg channels of group g at frame t
+// and keeps them in registers: a single pass over HBM, exact two-pass statistics (mean, then centred sum of squares)
+// combined across the T warps through shared memory. Lanes read adjacent cpg-float runs, i.e. whole rows coalesced.
+template <int CPG>
+__global__ void __launch_bounds__(512) gn_pixel_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
-                                                       int nb, int T, int P, int C, float eps, int act_silu) {
-  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp_global >= nb * P) return;
-  const int b = warp_global / P, p = warp_global - b * P;
-  const int cpg = C / GN_GROUPS;  // even (C % 64 == 0)
-  const size_t frame_stride = (size_t)P * C;
-  const float* x0 = x + ((size_t)b * T * P + p) * C + lane * cpg;
-  __nv_bfloat16* y0 = y + ((size_t)b * T * P + p) * C + lane * cpg;
-  // shifted single-pass moments (shift = first element of the group) for conditioning
-  const float K = x0[0];
-  float s = 0.f, q = 0.f;
-  for (int t = 0; t < T; ++t) {
-    const float2* r = reinterpret_cast<const float2*>(x0 + t * frame_stride);
-    for (int j = 0; j < cpg / 2; ++j) {
-      const float2 v = r[j];
-      const float d0 = v.x - K, d1 = v.y - K;
-      s += d0 + d1;
-      q += d0 * d0 + d1 * d1;
-    }
+                                                       int T, int P, int C, float eps, int act_silu) {
+  __shared__ float red[16][32];
+  const int t = threadIdx.x >> 5, g = threadIdx.x & 31;
+  const int b = blockIdx.x / P, p = blockIdx.x - b * P;
+  const size_t off = (((size_t)b * T + t) * P + p) * C + (size_t)g * CPG;
+  float v[CPG];
+  const float2* src = reinterpret_cast<const float2*>(x + off);
+#pragma unroll
+  for (int j = 0; j < CPG / 2; ++j) {
+    const float2 a = src[j];
+    v[2 * j] = a.x;
+    v[2 * j + 1] = a.y;
   }
-  const float n = (float)(T * cpg);
-  const float dm = s / n;
-  const float mean = K + dm;
-  const float var = fmaxf(q / n - dm * dm, 0.f);
-  const float rstd = rsqrtf(var + eps);
-  for (int t = 0; t < T; ++t) {
-    const float2* r = reinterpret_cast<const float2*>(x0 + t * frame_stride);
-    uint32_t* w = reinterpret_cast<uint32_t*>(y0 + t * frame_stride);
-    for (int j = 0; j < cpg / 2; ++j) {
-      const float2 v = r[j];
-      const int c = lane * cpg + 2 * j;
-      float a0 = (v.x - mean) * rstd * gamma[c] + beta[c];
-      float a1 = (v.y - mean) * rstd * gamma[c + 1] + beta[c + 1];
-      if (act_silu) { a0 = silu(a0); a1 = silu(a1); }
-      w[j] = pack_bf16x2(a0, a1);
-    }
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < CPG; ++j) s += v[j];
+  red[t][g] = s;
+  __syncthreads();
+  float tot = 0.f;
+  for (int k = 0; k < T; ++k) tot += red[k][g];
+  const float n = (float)(T * CPG);
+  const float mean = tot / n;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < CPG; ++j) {
+    const float d = v[j] - mean;
+    q += d * d;
+  }
+  __syncthreads();
+  red[t][g] = q;
+  __syncthreads();
+  float qt = 0.f;
+  for (int k = 0; k < T; ++k) qt += red[k][g];
+  const float rstd = rsqrtf(qt / n + eps);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(y + off);
+  const float2* g2 = reinterpret_cast<const float2*>(gamma + g * CPG);
+  const float2* b2 = reinterpret_cast<const float2*>(beta + g * CPG);
+#pragma unroll
+  for (int j = 0; j < CPG / 2; ++j) {
+    const float2 gm = g2[j], bt = b2[j];
+    float a0 = (v[2 * j] - mean) * rstd * gm.x + bt.x;
+    float a1 = (v[2 * j + 1] - mean) * rstd * gm.y + bt.y;
+    if (act_silu) { a0 = silu(a0); a1 = silu(a1); }
+    dst[j] = pack_bf16x2(a0, a1);
   }
 }
 
@@ -284,10 +294,21 @@ extern "C" int pn_groupnorm_pixel_silu(const float* x, const float* gamma, const
   PN_REQUIRE(channels % 64 == 0, "pn_groupnorm_pixel_silu: C=%lld must be a multiple of 64", (long long)channels);
   PN_REQUIRE(batch > 0 && frames_per_seq > 0 && pixels > 0, "pn_groupnorm_pixel_silu: empty input");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
-  const long long warps = batch * pixels;
-  const int blocks = (int)((warps * 32 + 255) / 256);
-  gn_pixel_kernel<<<blocks, 256, 0, st>>>(x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y_bf16), (int)batch,
-                                          (int)frames_per_seq, (int)pixels, (int)channels, eps, act_silu);
+  PN_REQUIRE(frames_per_seq <= 16, "pn_groupnorm_pixel_silu: T=%lld > 16 unsupported", (long long)frames_per_seq);
+  const long long blocks = batch * pixels;
+  PN_REQUIRE(blocks < (1ll << 31), "pn_groupnorm_pixel_silu: grid too large");
+  const int threads = (int)frames_per_seq * 32;
+  __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(y_bf16);
+  const int T = (int)frames_per_seq, P = (int)pixels, C = (int)channels;
+  switch (C / 32) {
+#define PN_GNP_CASE(CPG) case CPG: gn_pixel_kernel<CPG><<<(unsigned)blocks, threads, 0, st>>>(x, gamma, beta, y, T, P, C, eps, act_silu); break;
+    PN_GNP_CASE(2) PN_GNP_CASE(4) PN_GNP_CASE(6) PN_GNP_CASE(8) PN_GNP_CASE(10) PN_GNP_CASE(12) PN_GNP_CASE(16) PN_GNP_CASE(20)
+    PN_GNP_CASE(24) PN_GNP_CASE(30) PN_GNP_CASE(32) PN_GNP_CASE(40) PN_GNP_CASE(60) PN_GNP_CASE(80)
+#undef PN_GNP_CASE
+    default:
+      return fail(PN_ERR_UNSUPPORTED, "pn_groupnorm_pixel_silu: C=%lld (C/32=%lld channels per group) is not instantiated",
+                  (long long)channels, (long long)(channels / 32));
+  }
   PN_CHECK_CUDA(cudaGetLastError());
   return PN_OK;
 }
