@@ -28,7 +28,7 @@ constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle atom row
 // warp 0 TMA, warp 1 MMA, warps 2.. epilogue: 8 warps for the fp32/residual mode (168 registers each), 12 for the
 // ALU-heavy bf16 / GEGLU modes (the register file is granted per 4-warp group: 16 warps x 128 registers)
 constexpr bool gemm_streaming(int mode) { return mode == 4 || mode == 5; }
-constexpr int gemm_threads(int mode) { return (mode == 0 || mode == 3) ? 320 : gemm_streaming(mode) ? 352 : 448; }
+constexpr int gemm_threads(int mode) { return (mode == 0 || mode == 3 || mode == 6) ? 320 : gemm_streaming(mode) ? 352 : 448; }
 
 struct GemmParams {
   CUtensorMap mapA;
@@ -36,6 +36,7 @@ struct GemmParams {
   CUtensorMap mapOut;          // MODE 4 only: fp32 output / residual, box {32 floats, 128 rows}
   CUtensorMap mapRes;
   int has_res;
+  int halo_base_offset;        // MODE 6: encode (start >> 7) & 7 in the A descriptors (experiment switch)
   // geometry of the A tensor / output rows
   int NB, H, W;
   int tw, th, tn;             // tile box extents, tw*th*tn == 128
@@ -58,15 +59,20 @@ struct GemmParams {
 template <int BN, int STAGES, int NCTA, int MODE>
 struct GemmSmem {
   static constexpr int NEPI = gemm_streaming(MODE) ? 8 : gemm_threads(MODE) / 32 - 2;
-  static constexpr int STAGE_WARP_BYTES = (MODE == 0 || MODE == 3) ? 4096 : 2048;   // 32 rows x (128 | 64) B
+  static constexpr int STAGE_WARP_BYTES = (MODE == 0 || MODE == 3 || MODE == 6) ? 4096 : 2048;   // 32 rows x (128 | 64) B
+  // MODE 6 (haloed 3x3 conv): A ring of HALO_STAGES haloed tiles [(16+2) x (8+2) pixels x 64 ch], B ring of STAGES weight tiles
+  static constexpr int HALO_STAGES = 3;
+  static constexpr int A_HALO_BYTES = 23552;             // 18*10*128 = 23040, padded to a multiple of 1024
+  static constexpr int A_HALO_TX = 18 * 10 * 128;
   static constexpr int RCHUNK_BYTES = MODE == 5 ? 128 * 64 : 128 * 128;              // 128 rows x 32 (bf16 | fp32)
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / NCTA) * BK * 2;   // a CTA pair splits the N tile: each CTA stages BN/2 weight rows
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int RING_BYTES = MODE == 6 ? HALO_STAGES * A_HALO_BYTES + STAGES * B_BYTES : STAGES * STAGE_BYTES;
   static constexpr int STAGING_BYTES = gemm_streaming(MODE) ? (BN / 32) * RCHUNK_BYTES : NEPI * STAGE_WARP_BYTES;
   static constexpr int ROWMAP_BYTES = gemm_streaming(MODE) ? 0 : NEPI * 32 * 4;
-  static constexpr int BAR_BYTES = (2 * STAGES + 4 + 2 * (BN / 32)) * 8 + 16;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + STAGING_BYTES + ROWMAP_BYTES + BAR_BYTES + 1024;
+  static constexpr int BAR_BYTES = (2 * STAGES + 4 + 2 * (BN / 32) + 8) * 8 + 16;
+  static constexpr int TOTAL = RING_BYTES + STAGING_BYTES + ROWMAP_BYTES + BAR_BYTES + 1024;
 };
 
 // MODE: 0 = fp32 store (+ one fp32 residual), 1 = bf16 store, 2 = GEGLU (bf16 store of N/2 columns),
@@ -76,6 +82,9 @@ struct GemmSmem {
 //           (thread == row, conflict-free), and a dedicated warp TMA-stores it — no global LD/ST instruction and no
 //           register prefetch in the epilogue warps. Used for the HBM-bound K<=1280 linears and the temporal conv.
 //       5 = the same streaming epilogue with a bf16 store and no residual (q/k/v and query projections).
+//       6 = 3x3 conv with a HALOED A tile: the 9 taps of one 64-channel chunk are 9 row-shifted UMMA views of ONE
+//           (16+2)x(8+2)-pixel tile in shared memory, so the activations cross the L2->SM fabric once instead of 9
+//           times (the L2-bound N=160 tile of the level-0/1 convs); fp32 store through the generic epilogue.
 template <int BN, int STAGES, int NCTA, int MODE>
 __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using S = GemmSmem<BN, STAGES, NCTA, MODE>;
@@ -84,7 +93,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* stage_base = smem;
-  uint8_t* staging = smem + STAGES * S::STAGE_BYTES;
+  uint8_t* staging = smem + S::RING_BYTES;
   int* rowmap = reinterpret_cast<int*>(staging + S::STAGING_BYTES);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(rowmap) + S::ROWMAP_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -92,7 +101,9 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
   uint64_t* r_full = tmem_empty + 2;          // [BN/32]  MODE 4: tile chunk holds the residual / is free for the epilogue
   uint64_t* c_ready = r_full + BN / 32;       // [BN/32]  MODE 4: chunk updated by its 4 epilogue warps -> store it
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(c_ready + BN / 32);
+  uint64_t* a_full = c_ready + BN / 32;       // [3]      MODE 6: haloed A tiles
+  uint64_t* a_empty = a_full + 4;             // [3]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(a_empty + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -121,6 +132,12 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], NEPI * NCTA);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
+    if (MODE == 6) {
+      for (int i = 0; i < S::HALO_STAGES; ++i) {
+        mbar_init(&a_full[i], 1);
+        mbar_init(&a_empty[i], 1);
+      }
+    }
     if (gemm_streaming(MODE)) {
       tma_prefetch_desc(&p.mapOut);
       if (p.has_res) tma_prefetch_desc(&p.mapRes);
@@ -141,7 +158,95 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp == 0) {
+  if (warp == 0 && MODE == 6) {
+    // ===================== MODE 6 producer: one haloed A tile per 64-channel chunk, nine weight tiles per chunk ==========
+    if (lane == 0) {
+      uint8_t* ringA = stage_base;
+      uint8_t* ringB = stage_base + S::HALO_STAGES * S::A_HALO_BYTES;
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int tile = unit; tile < num_tiles; tile += num_units) {
+        const int tcol = tile % p.tiles_col;
+        int tm = (tile / p.tiles_col) * NCTA + (int)cta_rank;
+        const int twi = tm % p.tiles_w; tm /= p.tiles_w;
+        const int thi = tm % p.tiles_h; tm /= p.tiles_h;
+        const int x0 = twi * p.tw, y0 = thi * p.th, n0 = tm * p.tn;
+        for (int kc = 0; kc < p.kc_per_tap; ++kc) {
+          mbar_wait(&a_empty[sa], pa ^ 1);
+          if (NCTA == 2) {
+            if (cta_rank == 0) mbar_arrive_expect_tx(&a_full[sa], 2 * S::A_HALO_TX);
+            tma_load_4d_2sm(ringA + sa * S::A_HALO_BYTES, &p.mapA, &a_full[sa], kc * BK, x0 - 1, y0 - 1, n0);
+          } else {
+            mbar_arrive_expect_tx(&a_full[sa], S::A_HALO_TX);
+            tma_load_4d(ringA + sa * S::A_HALO_BYTES, &p.mapA, &a_full[sa], kc * BK, x0 - 1, y0 - 1, n0);
+          }
+          if (++sa == S::HALO_STAGES) { sa = 0; pa ^= 1; }
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&empty_bar[sb], pb ^ 1);
+            uint8_t* sB = ringB + sb * S::B_BYTES;
+            const int kcol = (tap * p.kc_per_tap + kc) * BK;
+            if (NCTA == 2) {
+              if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[sb], 2 * S::B_BYTES);
+              tma_load_2d_2sm(sB, &p.mapB, &full_bar[sb], kcol, tcol * BN + (int)cta_rank * (BN / 2));
+            } else {
+              mbar_arrive_expect_tx(&full_bar[sb], S::B_BYTES);
+              tma_load_2d(sB, &p.mapB, &full_bar[sb], kcol, tcol * BN);
+            }
+            if (++sb == STAGES) { sb = 0; pb ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && MODE == 6) {
+    // ===================== MODE 6 UMMA issuer: tap (dy,dx) = the A view shifted by dy*(tw+2)+dx rows ==========
+    if (cta_rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM * NCTA, BN, 0, 0);
+      const uint32_t ringA = smem_u32(stage_base);
+      const uint32_t ringB = ringA + S::HALO_STAGES * S::A_HALO_BYTES;
+      int sa = 0, sb = 0, acc = 0;
+      uint32_t pa = 0, pb = 0, acc_phase = 0;
+      for (int tile = unit; tile < num_tiles; tile += num_units) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kc = 0; kc < p.kc_per_tap; ++kc) {
+          mbar_wait(&a_full[sa], pa);
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&full_bar[sb], pb);
+            tc_fence_after();
+            if (lane == 0) {
+              const uint32_t rows = (uint32_t)((tap / 3) * 10 + (tap % 3));
+              const uint32_t sA = ringA + sa * S::A_HALO_BYTES + rows * 128;
+              const uint32_t sB = ringB + sb * S::B_BYTES;
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                const uint32_t aaddr = sA + k * 32;
+                const uint64_t da = umma_smem_desc_off(aaddr, 16, 1280, p.halo_base_offset ? (aaddr >> 7) & 7u : 0u);
+                const uint64_t db = umma_smem_desc(sB + k * 32, 16, 1024);
+                const uint32_t accum = (kc > 0 || tap > 0 || k > 0) ? 1u : 0u;
+                if (NCTA == 2) umma_f16_ss_2sm(d_tmem, da, db, idesc, accum);
+                else umma_f16_ss(d_tmem, da, db, idesc, accum);
+              }
+              const bool last = (kc == p.kc_per_tap - 1) && (tap == 8);
+              if (NCTA == 2) {
+                umma_commit_2sm(&empty_bar[sb], 3);
+                if (tap == 8) umma_commit_2sm(&a_empty[sa], 3);
+                if (last) umma_commit_2sm(&tmem_full[acc], 3);
+              } else {
+                umma_commit(&empty_bar[sb]);
+                if (tap == 8) umma_commit(&a_empty[sa]);
+                if (last) umma_commit(&tmem_full[acc]);
+              }
+            }
+            __syncwarp();
+            if (++sb == STAGES) { sb = 0; pb ^= 1; }
+          }
+          if (++sa == S::HALO_STAGES) { sa = 0; pa ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp == 0) {
     // ===================== TMA producer (every CTA loads its own A rows and its share of B) =====================
     if (lane == 0) {
       int stage = 0;
@@ -575,6 +680,15 @@ static int gemm_stream_kmax() {
   return kmax;
 }
 
+static int conv_halo_mode() {     // PN_CONV_HALO: 0 = off, 1 = on with base_offset (default), 2 = on with base_offset 0
+  static int m = -1;
+  if (m < 0) {
+    const char* e = getenv("PN_CONV_HALO");
+    m = e ? atoi(e) : 1;
+  }
+  return m;
+}
+
 static int gemm_mode_override() {
   static int mode = -1;
   if (mode < 0) {
@@ -699,6 +813,19 @@ extern "C" int pn_gemm(const pn_gemm_args* a, void* stream_v) {
   else if (a->N >= 128) BN = 128;
   else if (a->N > 32) BN = 64;
   else BN = 32;
+  // Haloed 3x3 conv (MODE 6): 16 x 8-pixel tiles, level-0/1 shapes whose N tile is 160 wide (L2->SM-bound otherwise).
+  bool halo_mode = conv_halo_mode() != 0 && a->taps_h == 3 && a->taps_w == 3 && !a->out_bf16 && !a->geglu &&
+                   a->residual == nullptr && a->residual2 == nullptr && a->N % 160 == 0 && a->N % 256 != 0 && H % 16 == 0 &&
+                   W % 8 == 0 && force != 1;
+  if (halo_mode) {
+    tw = 8; th = 16; tn = 1;
+    p.tw = tw; p.th = th; p.tn = tn;
+    p.tiles_w = (int)(W / 8); p.tiles_h = (int)(H / 16); p.tiles_n = (int)NB;
+    BN = 160;
+    const long long tiles_m_h = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
+    NCTA = (tiles_m_h * (a->N / 160) >= 2 * sm_count() || force == 2) ? 2 : 1;
+    p.halo_base_offset = conv_halo_mode() == 1 ? 1 : 0;
+  }
   // Streaming epilogue (MODE 4): fp32 output whose tile rows are consecutive output rows, short K loop (HBM-bound).
   const long long k_total = (long long)a->taps_h * a->taps_w * a->C;
   const bool rows_contig = (tw == 128 && th == 1 && tn == 1) && ((H == 1 && NB == 1) || (W % 128 == 0));
@@ -732,7 +859,7 @@ extern "C" int pn_gemm(const pn_gemm_args* a, void* stream_v) {
 
   const uint64_t dimsA[4] = {(uint64_t)a->C, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
   const uint64_t strA[3] = {(uint64_t)sw, (uint64_t)sh, (uint64_t)sn};
-  const uint32_t boxA[4] = {64u, (uint32_t)tw, (uint32_t)th, (uint32_t)tn};
+  const uint32_t boxA[4] = {64u, (uint32_t)(halo_mode ? tw + 2 : tw), (uint32_t)(halo_mode ? th + 2 : th), (uint32_t)tn};
   int rc = cached_tmap_bf16(&p.mapA, a->A, 4, dimsA, strA, boxA, 128);
   if (rc != PN_OK) return rc;
   const uint64_t K = (uint64_t)a->taps_h * a->taps_w * a->C;
@@ -743,6 +870,7 @@ extern "C" int pn_gemm(const pn_gemm_args* a, void* stream_v) {
   if (rc != PN_OK) return rc;
 
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  if (halo_mode) return NCTA == 2 ? launch_gemm_mode<160, 10, 2, 6>(p, stream) : launch_gemm_mode<160, 5, 1, 6>(p, stream);
   if (stream_mode && a->out_bf16) {
     if (NCTA == 2) return BN == 160 ? launch_gemm_mode<160, 6, 2, 5>(p, stream) : launch_gemm_mode<128, 7, 2, 5>(p, stream);
     return BN == 160 ? launch_gemm_mode<160, 5, 1, 5>(p, stream) : launch_gemm_mode<128, 6, 1, 5>(p, stream);

@@ -264,6 +264,12 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= 2ull << 61;  // SWIZZLE_128B
   return d;
 }
+// Same with an explicit base offset (bits [49,52)): needed when the tile does not start on a 1024-byte boundary of
+// the 128B swizzle pattern, e.g. a row-shifted view into a haloed conv tile: base_offset = (start >> 7) & 7.
+__device__ __forceinline__ uint64_t umma_smem_desc_off(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                       uint32_t base_offset) {
+  return umma_smem_desc(saddr, lbo_bytes, sbo_bytes) | (static_cast<uint64_t>(base_offset & 7u) << 49);
+}
 // Instruction descriptor, kind::f16: c=f32 (1<<4), a,b = bf16 (1<<7, 1<<10), majors, N>>3 at 17, M>>4 at 24.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(a_mn_major) << 15) | (uint32_t(b_mn_major) << 16) |

@@ -85,7 +85,9 @@ def test_gemm_strided_view(ops):
 
 
 @pytest.mark.parametrize("NB,H,W,C,N", [(2, 8, 24, 64, 160), (3, 4, 42, 128, 320), (2, 32, 336, 320, 320),
-                                        (4, 16, 168, 64, 64), (16, 4, 42, 64, 160)])
+                                        (4, 16, 168, 64, 64), (16, 4, 42, 64, 160),
+                                        # H % 16 == 0, W % 8 == 0, N % 160 == 0: the haloed-tile conv path (MODE 6)
+                                        (1, 16, 24, 64, 160), (2, 32, 40, 128, 320), (1, 48, 16, 64, 640), (3, 16, 168, 192, 640)])
 def test_conv3x3(ops, NB, H, W, C, N):
     x = _rand((NB, H, W, C), 15)
     w = _rand((N, C, 3, 3), 16, (9 * C) ** -0.5)
