@@ -152,56 +152,55 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
       }
     }
   } else if (warp == 1) {
-    // ===================== UMMA issuer =====================
-    const uint32_t idesc_s = umma_idesc_bf16(128, p.kv_n, 0, 0);      // S = Q K^T : both K-major
-    const uint32_t idesc_pv = umma_idesc_bf16(128, FA_D, 0, 1);       // PV: A = P K-major, B = V MN-major
-    const int ksteps_pv = p.kv_n / 16;
-    auto issue_pv = [&](int i) {
-      const int st = i % FA_STAGES, buf = i & 1;
-      mbar_wait(&v_full[st], (uint32_t)((i / FA_STAGES) & 1));
-      mbar_wait(&p_full[buf], (uint32_t)((i >> 1) & 1));
-      mbar_wait(&pv_empty[buf], (uint32_t)(((i >> 1) & 1) ^ 1));
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t sP = smem_u32(smem + FA_SMEM_P + buf * 2 * FA_TILE_BYTES);
-        const uint32_t sV = smem_u32(smem + FA_SMEM_V + st * FA_TILE_BYTES);
+    // ===================== UMMA issuer (one thread runs the whole loop; descriptors advance by integer adds) ====
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(128, p.kv_n, 0, 0);      // S = Q K^T : both K-major
+      const uint32_t idesc_pv = umma_idesc_bf16(128, FA_D, 0, 1);       // PV: A = P K-major, B = V MN-major
+      const int ksteps_pv = p.kv_n / 16;
+      const uint64_t dQ0 = umma_smem_desc(smem_u32(smem + FA_SMEM_Q), 16, 1024);
+      const uint64_t dK0 = umma_smem_desc(smem_u32(smem + FA_SMEM_K), 16, 1024);
+      const uint64_t dP0 = umma_smem_desc(smem_u32(smem + FA_SMEM_P), 16, 1024);
+      const uint64_t dV0 = umma_smem_desc(smem_u32(smem + FA_SMEM_V), 1024, 1024);
+      constexpr uint64_t TILE_STEP = FA_TILE_BYTES >> 4;                // start-address field is in 16-byte units
+      auto issue_pv = [&](int i) {
+        const int st = i % FA_STAGES, buf = i & 1;
+        mbar_wait(&v_full[st], (uint32_t)((i / FA_STAGES) & 1));
+        mbar_wait(&p_full[buf], (uint32_t)((i >> 1) & 1));
+        mbar_wait(&pv_empty[buf], (uint32_t)(((i >> 1) & 1) ^ 1));
+        tc_fence_after();
+        const uint64_t dP = dP0 + TILE_STEP * (2 * buf);
+        const uint64_t dV = dV0 + TILE_STEP * st;
         for (int k = 0; k < ksteps_pv; ++k) {
-          const uint64_t da = umma_smem_desc(sP + (k >> 2) * FA_TILE_BYTES + (k & 3) * 32, 16, 1024);
-          const uint64_t db = umma_smem_desc(sV + k * 2048, 1024, 1024);   // 16 keys (rows of 128 B) per K step
-          umma_f16_ss(tm_PV + buf * FA_D, da, db, idesc_pv, k > 0 ? 1u : 0u);
+          // P: 64-key tiles of 16 KB, 32 B per K step inside one; V: 16 keys (rows of 128 B) per K step
+          umma_f16_ss(tm_PV + buf * FA_D, dP + TILE_STEP * (k >> 2) + 2 * (k & 3), dV + 128 * k, idesc_pv,
+                      k > 0 ? 1u : 0u);
         }
         umma_commit(&pv_full[buf]);
         umma_commit(&kv_empty[st]);
-      }
-      __syncwarp();
-    };
-    int g = 0, it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const FaTile t = fa_decode(p, tile);
-      const int qb = it & 1;
-      const uint32_t sQ = smem_u32(smem + FA_SMEM_Q + qb * FA_TILE_BYTES);
-      mbar_wait(&q_full[qb], (uint32_t)((it >> 1) & 1));
-      for (int j = 0; j < t.nblk; ++j, ++g) {
-        const int st = g % FA_STAGES, buf = g & 1;
-        mbar_wait(&k_full[st], (uint32_t)((g / FA_STAGES) & 1));
-        mbar_wait(&s_empty[buf], (uint32_t)(((g >> 1) & 1) ^ 1));
-        tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sK = smem_u32(smem + FA_SMEM_K + st * FA_TILE_BYTES);
+      };
+      int g = 0, it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const FaTile t = fa_decode(p, tile);
+        const int qb = it & 1;
+        const uint64_t dQ = dQ0 + TILE_STEP * qb;
+        mbar_wait(&q_full[qb], (uint32_t)((it >> 1) & 1));
+        for (int j = 0; j < t.nblk; ++j, ++g) {
+          const int st = g % FA_STAGES, buf = g & 1;
+          mbar_wait(&k_full[st], (uint32_t)((g / FA_STAGES) & 1));
+          mbar_wait(&s_empty[buf], (uint32_t)(((g >> 1) & 1) ^ 1));
+          tc_fence_after();
+          const uint64_t dK = dK0 + TILE_STEP * st;
 #pragma unroll
-          for (int k = 0; k < FA_D / 16; ++k) {
-            const uint64_t da = umma_smem_desc(sQ + k * 32, 16, 1024);
-            const uint64_t db = umma_smem_desc(sK + k * 32, 16, 1024);
-            umma_f16_ss(tm_S + buf * 128, da, db, idesc_s, k > 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < FA_D / 16; ++k)
+            umma_f16_ss(tm_S + buf * 128, dQ + 2 * k, dK + 2 * k, idesc_s, k > 0 ? 1u : 0u);
           umma_commit(&s_full[buf]);
           if (j == t.nblk - 1) umma_commit(&q_empty[qb]);   // every S MMA reading this Q tile has retired
+          if (g > 0) issue_pv(g - 1);
         }
-        __syncwarp();
-        if (g > 0) issue_pv(g - 1);
       }
+      if (g > 0) issue_pv(g - 1);
     }
-    if (g > 0) issue_pv(g - 1);
+    __syncwarp();
   } else {
     // ===================== softmax / output warps =====================
     // Two threads per query row: warps w and w+4 share a TMEM lane quarter; the first takes the even 16-column

@@ -37,6 +37,7 @@ struct GemmParams {
   CUtensorMap mapRes;
   int has_res;
   int halo_base_offset;        // MODE 6: encode (start >> 7) & 7 in the A descriptors (experiment switch)
+  int debug;                   // PN_GEMM_DEBUG: 1 = no TMA loads after the first ring fill, 2 = no MMA issue (timing experiments)
   // geometry of the A tensor / output rows
   int NB, H, W;
   int tw, th, tn;             // tile box extents, tw*th*tn == 128
@@ -199,10 +200,14 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
     }
   } else if (warp == 1 && MODE == 6) {
     // ===================== MODE 6 UMMA issuer: tap (dy,dx) = the A view shifted by dy*(tw+2)+dx rows ==========
-    if (cta_rank == 0) {
+    if (cta_rank == 0 && lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM * NCTA, BN, 0, 0);
       const uint32_t ringA = smem_u32(stage_base);
       const uint32_t ringB = ringA + S::HALO_STAGES * S::A_HALO_BYTES;
+      // A view: 16 groups of 8 pixels, one image row (8+2 pixels, 1280 B) apart; base offset 0 (the 128B swizzle is
+      // a function of the absolute shared-memory address — verified on B200)
+      const uint64_t descA0 = umma_smem_desc(ringA, 16, 1280);
+      const uint64_t descB0 = umma_smem_desc(ringB, 16, 1024);
       int sa = 0, sb = 0, acc = 0;
       uint32_t pa = 0, pb = 0, acc_phase = 0;
       for (int tile = unit; tile < num_tiles; tile += num_units) {
@@ -211,34 +216,29 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kc = 0; kc < p.kc_per_tap; ++kc) {
           mbar_wait(&a_full[sa], pa);
+          const uint64_t da_tile = descA0 + (uint64_t)(S::A_HALO_BYTES >> 4) * sa;
+#pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(&full_bar[sb], pb);
             tc_fence_after();
-            if (lane == 0) {
-              const uint32_t rows = (uint32_t)((tap / 3) * 10 + (tap % 3));
-              const uint32_t sA = ringA + sa * S::A_HALO_BYTES + rows * 128;
-              const uint32_t sB = ringB + sb * S::B_BYTES;
+            const uint64_t da = da_tile + (uint64_t)(((tap / 3) * 10 + (tap % 3)) * 8);    // rows * 128 B / 16
+            const uint64_t db = descB0 + (uint64_t)(S::B_BYTES >> 4) * sb;
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) {
-                const uint32_t aaddr = sA + k * 32;
-                const uint64_t da = umma_smem_desc_off(aaddr, 16, 1280, p.halo_base_offset ? (aaddr >> 7) & 7u : 0u);
-                const uint64_t db = umma_smem_desc(sB + k * 32, 16, 1024);
-                const uint32_t accum = (kc > 0 || tap > 0 || k > 0) ? 1u : 0u;
-                if (NCTA == 2) umma_f16_ss_2sm(d_tmem, da, db, idesc, accum);
-                else umma_f16_ss(d_tmem, da, db, idesc, accum);
-              }
-              const bool last = (kc == p.kc_per_tap - 1) && (tap == 8);
-              if (NCTA == 2) {
-                umma_commit_2sm(&empty_bar[sb], 3);
-                if (tap == 8) umma_commit_2sm(&a_empty[sa], 3);
-                if (last) umma_commit_2sm(&tmem_full[acc], 3);
-              } else {
-                umma_commit(&empty_bar[sb]);
-                if (tap == 8) umma_commit(&a_empty[sa]);
-                if (last) umma_commit(&tmem_full[acc]);
-              }
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint32_t accum = (kc > 0 || tap > 0 || k > 0) ? 1u : 0u;
+              if (NCTA == 2) umma_f16_ss_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
+              else umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
             }
-            __syncwarp();
+            const bool last = (kc == p.kc_per_tap - 1) && (tap == 8);
+            if (NCTA == 2) {
+              umma_commit_2sm(&empty_bar[sb], 3);
+              if (tap == 8) umma_commit_2sm(&a_empty[sa], 3);
+              if (last) umma_commit_2sm(&tmem_full[acc], 3);
+            } else {
+              umma_commit(&empty_bar[sb]);
+              if (tap == 8) umma_commit(&a_empty[sa]);
+              if (last) umma_commit(&tmem_full[acc]);
+            }
             if (++sb == STAGES) { sb = 0; pb ^= 1; }
           }
           if (++sa == S::HALO_STAGES) { sa = 0; pa ^= 1; }
@@ -263,6 +263,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
           const int kc = kb - tap * p.kc_per_tap;
           const int dy = tap / p.taps_w - p.pad_h;
           const int dx = tap % p.taps_w - p.pad_w;
+          if (p.debug == 1 && (tile != unit || kb >= STAGES)) continue;   // experiment: the ring is filled once, never again
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = stage_base + stage * S::STAGE_BYTES;
           uint8_t* sB = sA + S::A_BYTES;
@@ -280,9 +281,15 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
       }
     }
   } else if (warp == 1) {
-    // ===================== UMMA issuer (leader CTA of a pair only) =====================
-    if (cta_rank == 0) {
+    // ===================== UMMA issuer (leader CTA of a pair only; ONE thread runs the whole loop) =====================
+    // The issue loop is the critical resource of the kernel (measured: ~150 instructions per k-block made every
+    // k-block cost ~650 cycles whatever the tile): descriptors are advanced by integer adds on precomputed 64-bit
+    // bases, no per-iteration election / warp sync, and only lane 0 polls the barriers.
+    if (cta_rank == 0 && lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM * NCTA, BN, 0, 0);
+      const uint64_t descA0 = umma_smem_desc(smem_u32(stage_base), 16, 1024);
+      const uint64_t descB0 = umma_smem_desc(smem_u32(stage_base) + S::A_BYTES, 16, 1024);
+      constexpr uint64_t STAGE_STEP = S::STAGE_BYTES >> 4;      // start-address field is in 16-byte units
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -292,28 +299,25 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          if (!(p.debug == 1 && (tile != unit || kb >= STAGES))) mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t sA = smem_u32(stage_base + stage * S::STAGE_BYTES);
-            const uint32_t sB = sA + S::A_BYTES;
+          const uint64_t da = descA0 + STAGE_STEP * stage;
+          const uint64_t db = descB0 + STAGE_STEP * stage;
+          if (p.debug != 2) {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
-              const uint64_t da = umma_smem_desc(sA + k * 32, 16, 1024);
-              const uint64_t db = umma_smem_desc(sB + k * 32, 16, 1024);
-              if (NCTA == 2) umma_f16_ss_2sm(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-              else umma_f16_ss(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            }
-            // commit: frees the smem slot (in both CTAs) once the MMAs retire; the last one also publishes the tile
-            if (NCTA == 2) {
-              umma_commit_2sm(&empty_bar[stage], 3);
-              if (kb == num_k_blocks - 1) umma_commit_2sm(&tmem_full[acc], 3);
-            } else {
-              umma_commit(&empty_bar[stage]);
-              if (kb == num_k_blocks - 1) umma_commit(&tmem_full[acc]);
+              if (NCTA == 2) umma_f16_ss_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              else umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
             }
           }
-          __syncwarp();
+          // commit: frees the smem slot (in both CTAs) once the MMAs retire; the last one also publishes the tile
+          if (NCTA == 2) {
+            umma_commit_2sm(&empty_bar[stage], 3);
+            if (kb == num_k_blocks - 1) umma_commit_2sm(&tmem_full[acc], 3);
+          } else {
+            umma_commit(&empty_bar[stage]);
+            if (kb == num_k_blocks - 1) umma_commit(&tmem_full[acc]);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -680,11 +684,30 @@ static int gemm_stream_kmax() {
   return kmax;
 }
 
-static int conv_halo_mode() {     // PN_CONV_HALO: 0 = off, 1 = on with base_offset (default), 2 = on with base_offset 0
+static int gemm_force_bn() {      // PN_GEMM_BN: force the N tile of the non-streaming CTA-pair path (experiments)
+  static int m = -1;
+  if (m < 0) {
+    const char* e = getenv("PN_GEMM_BN");
+    m = e ? atoi(e) : 0;
+  }
+  return m;
+}
+
+static int gemm_debug_mode() {
+  static int m = -1;
+  if (m < 0) {
+    const char* e = getenv("PN_GEMM_DEBUG");
+    m = e ? atoi(e) : 0;
+  }
+  return m;
+}
+
+static int conv_halo_mode() {     // PN_CONV_HALO: 0 = off, 2 = on, descriptor base_offset 0 (default; verified on B200: the
+                                   // 128B swizzle is a function of the absolute smem address), 1 = on with (start>>7)&7 (wrong)
   static int m = -1;
   if (m < 0) {
     const char* e = getenv("PN_CONV_HALO");
-    m = e ? atoi(e) : 1;
+    m = e ? atoi(e) : 2;
   }
   return m;
 }
@@ -795,6 +818,7 @@ extern "C" int pn_gemm(const pn_gemm_args* a, void* stream_v) {
   p.N = a->N;
   p.out = a->out; p.bias = a->bias; p.rowvec = a->rowvec; p.residual = a->residual;
   p.residual2 = a->residual2;
+  p.debug = gemm_debug_mode();
   p.ldo = a->ldo; p.ldr = a->ldr; p.ldr2 = a->ldr2;
   p.ldv = a->rowvec_ld > 0 ? a->rowvec_ld : a->N;
   p.rows_per_group = a->rows_per_group > 0 ? a->rows_per_group : 1;
@@ -813,6 +837,7 @@ extern "C" int pn_gemm(const pn_gemm_args* a, void* stream_v) {
   else if (a->N >= 128) BN = 128;
   else if (a->N > 32) BN = 64;
   else BN = 32;
+  if (gemm_force_bn() > 0 && a->N % 32 == 0) { BN = gemm_force_bn(); NCTA = 2; }
   // Haloed 3x3 conv (MODE 6): 16 x 8-pixel tiles, level-0/1 shapes whose N tile is 160 wide (L2->SM-bound otherwise).
   bool halo_mode = conv_halo_mode() != 0 && a->taps_h == 3 && a->taps_w == 3 && !a->out_bf16 && !a->geglu &&
                    a->residual == nullptr && a->residual2 == nullptr && a->N % 160 == 0 && a->N % 256 != 0 && H % 16 == 0 &&
@@ -879,6 +904,9 @@ extern "C" int pn_gemm(const pn_gemm_args* a, void* stream_v) {
     if (NCTA == 2) return BN == 160 ? launch_gemm_mode<160, 5, 2, 4>(p, stream) : launch_gemm_mode<128, 6, 2, 4>(p, stream);
     return BN == 160 ? launch_gemm_mode<160, 4, 1, 4>(p, stream) : launch_gemm_mode<128, 5, 1, 4>(p, stream);
   }
+  if (NCTA == 2 && BN == 192) return launch_gemm<192, 6, 2>(p, stream);
+  if (NCTA == 2 && BN == 128) return launch_gemm<128, 7, 2>(p, stream);
+  if (NCTA == 2 && BN == 64) return launch_gemm<64, 8, 2>(p, stream);
   if (NCTA == 2) return BN == 256 ? launch_gemm<256, 6, 2>(p, stream) : launch_gemm<160, 7, 2>(p, stream);
   switch (BN) {
     case 160: return launch_gemm<160, 5, 1>(p, stream);
