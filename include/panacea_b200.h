@@ -43,8 +43,8 @@ int pn_abi_version(void);
  * 468-476), 1x1 skip / zero convs (openaimodel.py:486; controlmodel.py:81-84).
  *   out[row, n] = epi( sum_{th,tw,c} A[nb, y+th-taps_h/2, x+tw-taps_w/2, c] * B[n, (th*taps_w+tw)*C + c] )
  * with zero padding outside [0,H)x[0,W) and row = (nb*H + y)*W + x.
- * epi: + bias[n] + rowvec[(row / rows_per_group) % n_groups, n]; GEGLU (interleaved value/gate columns ->
- * N/2 outputs, attention.py:91-99); + residual[row, n] + residual2[row, n] (fp32); store fp32 or bf16.
+ * epi: + bias[n] + rowvec[(row / rows_per_group) % n_groups, n]; GEGLU (columns in blocks of 32 = 16 value
+ * columns then the 16 gate columns of the same outputs -> N/2 outputs, out = value * gelu_erf(gate), attention.py:91-99); + residual[row, n] + residual2[row, n] (fp32); store fp32 or bf16.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct pn_gemm_args {
   const void* A;          /* bf16 [NB, H, W, C] with element strides below (C contiguous) */

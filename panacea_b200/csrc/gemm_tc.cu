@@ -37,7 +37,8 @@ struct GemmParams {
   CUtensorMap mapRes;
   int has_res;
   int halo_base_offset;        // MODE 6: encode (start >> 7) & 7 in the A descriptors (experiment switch)
-  int debug;                   // PN_GEMM_DEBUG: 1 = no TMA loads after the first ring fill, 2 = no MMA issue (timing experiments)
+  int debug;                   // PN_GEMM_DEBUG (timing experiments): 1 = no TMA loads after the first ring fill, 2 = no MMA issue,
+                               // 3 = epilogue reads TMEM only, 4 = no global stores
   // geometry of the A tensor / output rows
   int NB, H, W;
   int tw, th, tn;             // tile box extents, tw*th*tn == 128
@@ -356,11 +357,17 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
           nm0 = (t2 * p.H + h2) * p.W + w2 * p.tw;
           nn0 = (ntile % p.tiles_col) * BN;
         }
+        // all chunk stores are issued back to back (one bulk group each); a chunk's buffer is only handed on once
+        // ITS group has been read out of shared memory — waiting per store serialised the store warp
+#pragma unroll
         for (int c = 0; c < NCH; ++c) {
           mbar_wait(&c_ready[c], (uint32_t)(it & 1));
-          tma_store_2d(&p.mapOut, staging + c * S::RCHUNK_BYTES, n0 + c * 32, m0);
+          if (p.debug != 4) tma_store_2d(&p.mapOut, staging + c * S::RCHUNK_BYTES, n0 + c * 32, m0);
           tma_store_commit();
-          tma_store_wait_read();                       // the chunk has left shared memory: reuse it for the next tile
+        }
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          tma_store_wait_read_le(NCH - 1 - c);         // groups complete in order: chunk c has left shared memory
           if (ntile < num_tiles) {
             if (p.has_res) {
               mbar_arrive_expect_tx(&r_full[c], S::RCHUNK_BYTES);
@@ -429,7 +436,8 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
             }
           }
           mbar_wait(&r_full[c], (uint32_t)(it & 1));
-          if (MODE == 5) {
+          if (p.debug == 3) {
+          } else if (MODE == 5) {
             // 32 bf16 = 64 B per row; TMA SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3
             uint8_t* rowp = staging + c * S::RCHUNK_BYTES + r * 64;
 #pragma unroll
@@ -536,6 +544,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
             __syncwarp();
             if (lane == 0) release_acc(acc);
           }
+          if (p.debug == 3) continue;
           const int n0 = n_base + c * 32;
           float f[32];
 #pragma unroll
@@ -545,7 +554,8 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
             for (int j = 0; j < 32; j += 4) {
               if (n0 + j < p.N) {
                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-                f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                f2_unpack(f2_add(f2_pack(f[j], f[j + 1]), f2_pack(b4.x, b4.y)), f[j], f[j + 1]);
+                f2_unpack(f2_add(f2_pack(f[j + 2], f[j + 3]), f2_pack(b4.z, b4.w)), f[j + 2], f[j + 3]);
               }
             }
           }
@@ -555,15 +565,19 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
             for (int j = 0; j < 32; j += 4) {
               if (n0 + j < p.N) {
                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(rv + n0 + j));
-                f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                f2_unpack(f2_add(f2_pack(f[j], f[j + 1]), f2_pack(b4.x, b4.y)), f[j], f[j + 1]);
+                f2_unpack(f2_add(f2_pack(f[j + 2], f[j + 3]), f2_pack(b4.z, b4.w)), f[j + 2], f[j + 3]);
               }
             }
           }
           if (MODE == 2) {
-            // packed weight rows are interleaved (value, gate) pairs: out[n/2] = value * gelu(gate)
-            // (reference GEGLU: attention.py:97-99, chunk order value-first, exact erf GELU)
+            // chunk = 16 value columns then the 16 gate columns of the same outputs: out = value * gelu_erf(gate)
+            // (reference GEGLU: attention.py:97-99, exact erf GELU); two outputs per packed fp32x2 instruction
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = f[2 * j] * gelu_erf_fast(f[2 * j + 1]);
+            for (int j = 0; j < 8; ++j) {
+              const f32x2 o = geglu_f32x2(f2_pack(f[2 * j], f[2 * j + 1]), f2_pack(f[16 + 2 * j], f[16 + 2 * j + 1]));
+              f2_unpack(o, f[2 * j], f[2 * j + 1]);
+            }
             uint4* dst = reinterpret_cast<uint4*>(my_stage + lane * 32);   // 16 bf16 = 32 B per row
             dst[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
             dst[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
@@ -575,7 +589,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
               const int rr = i * 16 + (lane >> 1);
               const int ch = lane & 1;
               const int grow = my_rowmap[rr];
-              if (grow >= 0 && no0 + ch * 8 < p.N / 2) {
+              if (grow >= 0 && no0 + ch * 8 < p.N / 2 && p.debug != 4) {
                 const uint4 val = *reinterpret_cast<const uint4*>(my_stage + rr * 32 + ch * 16);
                 *reinterpret_cast<uint4*>(out + (long long)grow * p.ldo + no0 + ch * 8) = val;
               }
@@ -597,7 +611,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
               const int rr = i * 8 + (lane >> 2);
               const int ch = lane & 3;
               const int grow = my_rowmap[rr];
-              if (grow >= 0 && n0 + ch * 8 < p.N) {
+              if (grow >= 0 && n0 + ch * 8 < p.N && p.debug != 4) {
                 const int sw = ch ^ ((rr >> 1) & 3);
                 uint4 val = *reinterpret_cast<const uint4*>(my_stage + rr * 64 + sw * 16);
                 if (p.residual != nullptr) {
@@ -641,7 +655,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
             for (int i = 0; i < 8; ++i) {
               const int rr = i * 4 + (lane >> 3);
               const int grow = my_rowmap[rr];
-              if (grow >= 0 && col_ok) {
+              if (grow >= 0 && col_ok && p.debug != 4) {
                 const int sw = ch ^ (rr & 7);
                 float4 val = *reinterpret_cast<const float4*>(my_stage + rr * 128 + sw * 16);
                 if (pre) {

@@ -117,6 +117,21 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read_n() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+// at most n of the most recent bulk groups may still be reading shared memory (n folds to an immediate when unrolled)
+__device__ __forceinline__ void tma_store_wait_read_le(int n) {
+  switch (n) {
+    case 0: tma_store_wait_read_n<0>(); break;
+    case 1: tma_store_wait_read_n<1>(); break;
+    case 2: tma_store_wait_read_n<2>(); break;
+    case 3: tma_store_wait_read_n<3>(); break;
+    case 4: tma_store_wait_read_n<4>(); break;
+    case 5: tma_store_wait_read_n<5>(); break;
+    case 6: tma_store_wait_read_n<6>(); break;
+    default: tma_store_wait_read_n<7>(); break;
+  }
+}
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------------------------
@@ -198,7 +213,7 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t saddr, uint32_t rank) {
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_saddr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_saddr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_saddr) : "memory");
 }
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the CTA-pair peer bit: address the even CTA's copy
 // TMA loads issued by either CTA of a pair; the transaction bytes complete on the LEADER CTA's mbarrier.
@@ -315,6 +330,60 @@ __device__ __forceinline__ float erf_fast(float x) {
   return copysignf(r, x);
 }
 __device__ __forceinline__ float gelu_erf_fast(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f)); }
+
+// ---- packed fp32 pairs (sm_100 FFMA2/FMUL2/FADD2: two lanes of fp32 math per issue slot) ----
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 f2_splat(float x) { return f2_pack(x, x); }
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// value * gelu_erf(gate) on two (value, gate) pairs at once. gelu(g) = g * Phi(g), Phi(g) = 1 - q for g >= 0 and q for
+// g < 0 with q = 0.5 * erfc(|g| / sqrt2) = 0.5 * poly(t) * exp(-g^2/2), t = 1 / (1 + p |g| / sqrt2)  (Abramowitz &
+// Stegun 7.1.26, |abs error of erf| <= 1.5e-7), hence  g * Phi(g) = 0.5 g + |g| (0.5 - q).
+__device__ __forceinline__ f32x2 geglu_f32x2(f32x2 value, f32x2 gate) {
+  const f32x2 ag = gate & 0x7FFFFFFF7FFFFFFFull;
+  const f32x2 d = f2_fma(ag, f2_splat(0.3275911f * 0.70710678118654752f), f2_splat(1.0f));
+  float d0, d1;
+  f2_unpack(d, d0, d1);
+  const f32x2 t = f2_pack(rcp_approx(d0), rcp_approx(d1));
+  // exp(-g^2/2) = 2^(-(g * sqrt(log2(e)/2))^2); the negation rides on the MUFU operand
+  const f32x2 sg = f2_mul(gate, f2_splat(0.84932180028801905f));
+  const f32x2 m = f2_mul(sg, sg);
+  float m0, m1;
+  f2_unpack(m, m0, m1);
+  const f32x2 e = f2_pack(ex2_approx(-m0), ex2_approx(-m1));
+  // -q / e = -0.5 * (a1 t + ... + a5 t^5)
+  f32x2 poly = f2_fma(f2_splat(-0.5f * 1.061405429f), t, f2_splat(-0.5f * -1.453152027f));
+  poly = f2_fma(poly, t, f2_splat(-0.5f * 1.421413741f));
+  poly = f2_fma(poly, t, f2_splat(-0.5f * -0.284496736f));
+  poly = f2_fma(poly, t, f2_splat(-0.5f * 0.254829592f));
+  poly = f2_mul(poly, t);
+  const f32x2 r = f2_fma(poly, e, f2_splat(0.5f));                              // 0.5 - q
+  const f32x2 gelu = f2_fma(gate, f2_splat(0.5f), f2_mul(ag, r));
+  return f2_mul(value, gelu);
+}
+
 __device__ __forceinline__ float silu(float x) { return x * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
 
 }  // namespace pn

@@ -19,6 +19,7 @@ import math
 
 import torch
 
+from .ops import geglu_pack
 from .netplan import (CROSS_VIEW_NEIGHBOURS, HINT_STRIDES, STT_BRANCHES, NetConfig, Plan, Stage, make_plan)
 
 F32 = torch.float32
@@ -109,10 +110,10 @@ class Engine:
                     for a in ("attn1", "attn2"):
                         W[f"{t}.{a}.o.w"] = P[f"{t}.{a}.to_out.0.weight"].detach().to(dt).contiguous()
                         W[f"{t}.{a}.o.b"] = f(P[f"{t}.{a}.to_out.0.bias"])
-                    # GEGLU: interleave (value_j, gate_j) rows so one N-tile holds both halves of a column pair
+                    # GEGLU: 16 value rows then their 16 gate rows, so one accumulator chunk holds both halves
                     w1, b1 = P[t + ".ff.net.0.proj.weight"].detach(), P[t + ".ff.net.0.proj.bias"].detach()
-                    W[t + ".ff1.w"] = torch.stack([w1[:4 * c], w1[4 * c:]], 1).reshape(8 * c, c).to(dt).contiguous()
-                    W[t + ".ff1.b"] = torch.stack([b1[:4 * c], b1[4 * c:]], 1).reshape(8 * c).to(F32).contiguous()
+                    W[t + ".ff1.w"] = geglu_pack(w1).to(dt).contiguous()
+                    W[t + ".ff1.b"] = geglu_pack(b1).to(F32).contiguous()
                     W[t + ".ff2.w"] = P[t + ".ff.net.2.weight"].detach().to(dt).contiguous(); W[t + ".ff2.b"] = f(P[t + ".ff.net.2.bias"])
             elif st.kind == "down":
                 W[k + ".w"] = _pack_conv3(P[k + ".op.weight"].detach(), dt); W[k + ".b"] = f(P[k + ".op.bias"])

@@ -28,6 +28,17 @@ def _req(cond, msg):
         raise ValueError(msg)
 
 
+def geglu_pack(t: torch.Tensor) -> torch.Tensor:
+    """Row layout the GEGLU epilogue of pn_gemm expects, from the reference's [value rows | gate rows] layout
+    (GEGLU.proj, attention.py:94-99): blocks of 32 rows = 16 value rows then the 16 gate rows of the same outputs,
+    so one 32-column accumulator chunk holds both halves of 16 outputs (and packs into f32x2 register pairs)."""
+    half = t.shape[0] // 2
+    _req(t.shape[0] % 32 == 0, "geglu_pack: 2*inner must be a multiple of 32")
+    v = t[:half].reshape(half // 16, 16, *t.shape[1:])
+    g = t[half:].reshape(half // 16, 16, *t.shape[1:])
+    return torch.stack([v, g], 1).reshape(t.shape).contiguous()
+
+
 class NativeOps:
     """The production op set. `launches` counts kernel launches issued through the C ABI."""
 

@@ -3,6 +3,8 @@ import pytest
 import torch
 import torch.nn.functional as F
 
+from panacea_b200.ops import geglu_pack
+
 pytestmark = pytest.mark.gpu
 
 # the torch references below must be true fp32 (cuDNN/cuBLAS default to TF32 for conv/matmul on this GPU)
@@ -66,8 +68,7 @@ def test_gemm_geglu(ops):
     a = _rand((M, C), 10)
     w = _rand((8 * C, C), 11, C ** -0.5)       # reference layout: rows [0,4C) value, [4C,8C) gate
     b = _rand((8 * C,), 12, dtype=torch.float32)
-    wi = torch.stack([w[:4 * C], w[4 * C:]], 1).reshape(8 * C, C).contiguous()
-    bi = torch.stack([b[:4 * C], b[4 * C:]], 1).reshape(8 * C).contiguous()
+    wi, bi = geglu_pack(w), geglu_pack(b)
     out = ops.gemm(a, wi, bias=bi, geglu=True, out_dtype=torch.bfloat16)
     torch.cuda.synchronize()
     y = a.float() @ w.float().t() + b

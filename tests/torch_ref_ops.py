@@ -44,7 +44,8 @@ class TorchRefOps:
             grp = (torch.arange(rows) // rows_per_group) % n_groups
             y = y + rowvec[grp]
         if geglu:
-            y = y[:, 0::2] * F.gelu(y[:, 1::2])
+            y3 = y.reshape(rows, -1, 2, 16)          # packed layout: 16 value columns, then their 16 gate columns
+            y = (y3[:, :, 0] * F.gelu(y3[:, :, 1])).reshape(rows, -1)
         if residual is not None:
             y = y + residual.reshape(rows, -1)
         if residual2 is not None:
