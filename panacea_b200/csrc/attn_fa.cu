@@ -9,14 +9,18 @@
 //   * text cross-attention (attention.py:229-291, 77 keys): V=1, one K/V block per batch element, tail masked.
 // (Temporal self-attention over T<=16 frames is a CUDA-core kernel, attn_small.cu.)
 //
-// CTA = one query tile (<=128 queries of one frame/view/head). Warp roles:
-//   warp 0: TMA producer (Q once; K and V boxes through a 3-stage ring)
-//   warp 1: UMMA issuer   S = Q K^T  (M=128, N=kv_n, K=64)  -> TMEM, double buffered
-//                         PV = P V   (M=128, N=64,  K=kv_n) -> TMEM, double buffered (V is the MN-major B operand)
-//   warps 2-9: softmax, two threads per query row (TMEM lane == row; the pair splits the S columns and the
-//              output channels): tcgen05.ld S once -> running max (pair exchange through smem) -> exp2 -> bf16 P
-//              into 128B-swizzled smem (A operand of PV); O accumulates in registers with the usual rescale; the
-//              PV of block j-1 is folded in while the tensor core works on block j.
+// CTA = a PAIR of query tiles (<=128 queries each, consecutive tiles of one frame/view/head) that share the K/V
+// stream, one softmax warpgroup per tile so the two tiles' dependency chains interleave on the tensor core and the
+// MUFU. Warp roles:
+//   warp 0: TMA producer (Q pair, double buffered across work items; K and V boxes through a 4-stage ring)
+//   warp 1: UMMA issuer   S_t = Q_t K^T  (M=128, N=kv_n, K=64)  SS form -> TMEM
+//                         O_t (+)= P_t V (M=128, N=64,  K=kv_n) TS form: P is read from TENSOR MEMORY, V is the
+//                                                               MN-major B operand; O accumulates in TMEM
+//   warps 2-5 / 6-9: softmax group of tile A / B, ONE thread per query row (TMEM lane == row): tcgen05.ld S ->
+//              row max -> exp2 -> bf16 P written back to TMEM (tcgen05.st); the running maximum is only raised when
+//              it grew by more than 2^8 (lazy rescale, exact: l and O always share one reference maximum), and the
+//              rare rescale of O is done in place in TMEM by the row's own thread. The normalise-and-store epilogue
+//              of a work item runs inside the first block of the next one, behind that block's S MMA.
 #include "common.cuh"
 #include "ptx.cuh"
 #include "../../include/panacea_b200.h"
@@ -24,16 +28,17 @@
 namespace pn {
 
 constexpr int FA_D = 64;
-constexpr int FA_STAGES = 3;
-constexpr int FA_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 softmax
+constexpr int FA_STAGES = 4;
+constexpr int FA_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..5 softmax of tile A, 6..9 of tile B
 constexpr int FA_TILE_BYTES = 128 * 128;          // 128 rows x 64 bf16
-constexpr int FA_SMEM_Q = 0;                                        // 2 query tiles (double buffered across tiles)
-constexpr int FA_SMEM_K = 2 * FA_TILE_BYTES;
+constexpr int FA_SMEM_Q = 0;                                        // [2 buffers][2 tiles]
+constexpr int FA_SMEM_K = 4 * FA_TILE_BYTES;
 constexpr int FA_SMEM_V = FA_SMEM_K + FA_STAGES * FA_TILE_BYTES;
-constexpr int FA_SMEM_P = FA_SMEM_V + FA_STAGES * FA_TILE_BYTES;   // 2 buffers x 2 atoms x 16 KB
-constexpr int FA_SMEM_BAR = FA_SMEM_P + 4 * FA_TILE_BYTES;
-constexpr int FA_SMEM_XCH = FA_SMEM_BAR + 256;                      // row-max exchange [2][2][128] + row-sum exchange [2][128]
-constexpr int FA_SMEM_TOTAL = FA_SMEM_XCH + (2 * 2 * 128 + 2 * 128) * 4 + 1024;
+constexpr int FA_SMEM_BAR = FA_SMEM_V + FA_STAGES * FA_TILE_BYTES;
+constexpr int FA_SMEM_TOTAL = FA_SMEM_BAR + 512 + 1024;
+// tensor memory columns: S_A S_B (fp32, 128 each) | P_A P_B (bf16 pairs, 64 each) | O_A O_B (fp32, 64 each)
+constexpr uint32_t FA_TM_S = 0, FA_TM_P = 256, FA_TM_O = 384;
+constexpr float FA_LAZY_LOG2 = 8.0f;              // raise the reference maximum only when it grew by more than 2^8
 
 struct FaParams {
   CUtensorMap mapQ;
@@ -42,37 +47,38 @@ struct FaParams {
   int heads;
   int F, H, V, W;              // query token grid
   int qw, qh, tiles_x, tiles_y;
+  int tiles_per_group, pairs;  // query tiles of one (frame, view, head) and pairs of them
   int kw, kh, kv_rows, kv_n, kv_yblocks;
   int kv_views[8][2];
   int kv_view_count[8];
   int kv_frame_div;            // kv frame = q frame / kv_frame_div
-  int total_tiles;
+  int total_items;
   float scale_log2;            // softmax scale * log2(e)
   __nv_bfloat16* out;
   long long out_ld;            // token stride of out (elements)
 };
 
-struct FaTile {
-  int x0, y0, head, view, frame, nblk;
+struct FaItem {
+  int t0, head, view, frame, nblk;
+  bool has_b;
 };
 
-// q tile fastest, then head, view, frame: CTAs that run concurrently share K/V in L2
-__device__ __forceinline__ FaTile fa_decode(const FaParams& p, int tile) {
-  FaTile t;
-  const int tx = tile % p.tiles_x; tile /= p.tiles_x;
-  const int ty = tile % p.tiles_y; tile /= p.tiles_y;
-  t.head = tile % p.heads; tile /= p.heads;
-  t.view = tile % p.V; tile /= p.V;
-  t.frame = tile;
-  t.x0 = tx * p.qw;
-  t.y0 = ty * p.qh;
+// pair fastest, then head, view, frame: CTAs that run concurrently share K/V in L2
+__device__ __forceinline__ FaItem fa_decode(const FaParams& p, int item) {
+  FaItem t;
+  const int pr = item % p.pairs; item /= p.pairs;
+  t.head = item % p.heads; item /= p.heads;
+  t.view = item % p.V; item /= p.V;
+  t.frame = item;
+  t.t0 = 2 * pr;
+  t.has_b = (t.t0 + 1) < p.tiles_per_group;
   t.nblk = p.kv_view_count[t.view] * p.kv_yblocks;
   return t;
 }
 
-// Persistent kernel: each CTA walks a strided list of query tiles; the K/V-block pipeline (S and PV double buffers,
-// 3-stage K/V ring) runs ACROSS tile boundaries, so the prologue, the Q load and the last PV of a tile hide behind the
-// next tile's work (this is what makes the 1-block text attention and the 16-block view attention share one kernel).
+// Persistent kernel: each CTA walks a strided list of work items; the K/V-block pipeline runs ACROSS item boundaries
+// (Q double buffer, deferred epilogue), which is what lets the 1-block text attention and the 16/32-block view attention
+// share one kernel.
 // MASK: the key block has padding columns (kv_rows < kv_n, e.g. 77 text keys in an 80-wide block) that must get p = 0.
 // NCH: number of 16-column chunks of a key block (kv_n / 16) fixed at compile time for the shapes of the network
 // (7 = 112 keys per block at 32x56 views, 8 = 128 keys at 32x64 views, 5 = the 77 text keys, 2 = the 4x7 middle block);
@@ -84,15 +90,14 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FA_SMEM_BAR);
   uint64_t* q_full = bars;                     // [2]
   uint64_t* q_empty = bars + 2;                // [2]
-  uint64_t* k_full = bars + 4;                 // [3]
-  uint64_t* v_full = bars + 7;                 // [3]
-  uint64_t* kv_empty = bars + 10;              // [3]
-  uint64_t* s_full = bars + 13;                // [2]
-  uint64_t* s_empty = bars + 15;               // [2]
-  uint64_t* p_full = bars + 17;                // [2]
-  uint64_t* pv_full = bars + 19;               // [2]
-  uint64_t* pv_empty = bars + 21;              // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 23);
+  uint64_t* k_full = bars + 4;                 // [FA_STAGES]
+  uint64_t* v_full = bars + 8;                 // [FA_STAGES]
+  uint64_t* kv_empty = bars + 12;              // [FA_STAGES]
+  uint64_t* s_full = bars + 16;                // [2 tiles]  S_t written by the tensor core
+  uint64_t* s_free = bars + 18;                // [2]        S_t copied to registers by its softmax group
+  uint64_t* p_full = bars + 20;                // [2]        P_t (and a rescaled O_t) complete in tensor memory
+  uint64_t* pv_done = bars + 22;               // [2]        O_t (+)= P_t V retired: P_t and O_t may be touched again
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -100,7 +105,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
   // zero Q/K/V staging once: rows a TMA box does not cover (kv_rows..kv_n) must read as 0, never as stale NaNs
   {
     uint4* z = reinterpret_cast<uint4*>(smem);
-    for (int i = threadIdx.x; i < FA_SMEM_P / 16; i += FA_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < FA_SMEM_BAR / 16; i += FA_THREADS) z[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
   }
   if (warp == 0 && lane == 0) {
@@ -111,10 +116,9 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
     for (int i = 0; i < FA_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&kv_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 8);      // one elected arrive per softmax warp
-      mbar_init(&p_full[i], 8);
-      mbar_init(&pv_full[i], 1);
-      mbar_init(&pv_empty[i], 8);
+      mbar_init(&s_free[i], 4);       // one elected arrive per warp of the tile's softmax group
+      mbar_init(&p_full[i], 4);
+      mbar_init(&pv_done[i], 1);
     }
     fence_barrier_init();
   }
@@ -123,8 +127,6 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const uint32_t tm_S = tmem_base;          // 2 x 128 columns
-  const uint32_t tm_PV = tmem_base + 256;   // 2 x 64 columns
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -132,12 +134,16 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
       const uint32_t q_bytes = (uint32_t)(p.qw * p.qh) * 128u;
       const uint32_t kv_bytes = (uint32_t)p.kv_rows * 128u;
       int g = 0, it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const FaTile t = fa_decode(p, tile);
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+        const FaItem t = fa_decode(p, item);
         const int qb = it & 1;
         mbar_wait(&q_empty[qb], (uint32_t)(((it >> 1) & 1) ^ 1));
-        mbar_arrive_expect_tx(&q_full[qb], q_bytes);
-        tma_load_5d(smem + FA_SMEM_Q + qb * FA_TILE_BYTES, &p.mapQ, &q_full[qb], t.head * FA_D, t.x0, t.view, t.y0, t.frame);
+        mbar_arrive_expect_tx(&q_full[qb], t.has_b ? 2 * q_bytes : q_bytes);
+        for (int sl = 0; sl < (t.has_b ? 2 : 1); ++sl) {
+          const int ti = t.t0 + sl;
+          tma_load_5d(smem + FA_SMEM_Q + (qb * 2 + sl) * FA_TILE_BYTES, &p.mapQ, &q_full[qb], t.head * FA_D,
+                      (ti % p.tiles_x) * p.qw, t.view, (ti / p.tiles_x) * p.qh, t.frame);
+        }
         const int kv_frame = t.frame / p.kv_frame_div;
         for (int j = 0; j < t.nblk; ++j, ++g) {
           const int st = g % FA_STAGES;
@@ -155,193 +161,195 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
     // ===================== UMMA issuer (one thread runs the whole loop; descriptors advance by integer adds) ====
     if (lane == 0) {
       const uint32_t idesc_s = umma_idesc_bf16(128, p.kv_n, 0, 0);      // S = Q K^T : both K-major
-      const uint32_t idesc_pv = umma_idesc_bf16(128, FA_D, 0, 1);       // PV: A = P K-major, B = V MN-major
+      const uint32_t idesc_pv = umma_idesc_bf16(128, FA_D, 0, 1);       // PV: A = P (tensor memory), B = V MN-major
       const int ksteps_pv = p.kv_n / 16;
       const uint64_t dQ0 = umma_smem_desc(smem_u32(smem + FA_SMEM_Q), 16, 1024);
       const uint64_t dK0 = umma_smem_desc(smem_u32(smem + FA_SMEM_K), 16, 1024);
-      const uint64_t dP0 = umma_smem_desc(smem_u32(smem + FA_SMEM_P), 16, 1024);
       const uint64_t dV0 = umma_smem_desc(smem_u32(smem + FA_SMEM_V), 1024, 1024);
       constexpr uint64_t TILE_STEP = FA_TILE_BYTES >> 4;                // start-address field is in 16-byte units
-      auto issue_pv = [&](int i) {
-        const int st = i % FA_STAGES, buf = i & 1;
-        mbar_wait(&v_full[st], (uint32_t)((i / FA_STAGES) & 1));
-        mbar_wait(&p_full[buf], (uint32_t)((i >> 1) & 1));
-        mbar_wait(&pv_empty[buf], (uint32_t)(((i >> 1) & 1) ^ 1));
-        tc_fence_after();
-        const uint64_t dP = dP0 + TILE_STEP * (2 * buf);
+      uint32_t n_s[2] = {0, 0}, n_pv[2] = {0, 0};                       // blocks issued per tile slot
+      bool pend = false, pend_b = false;
+      int pend_g = 0, pend_j = 0;
+      // O_t (+)= P_t V of the block issued one iteration earlier (its softmax ran while the next S was computed)
+      auto issue_pv = [&]() {
+        const int st = pend_g % FA_STAGES;
+        mbar_wait(&v_full[st], (uint32_t)((pend_g / FA_STAGES) & 1));
         const uint64_t dV = dV0 + TILE_STEP * st;
-        for (int k = 0; k < ksteps_pv; ++k) {
-          // P: 64-key tiles of 16 KB, 32 B per K step inside one; V: 16 keys (rows of 128 B) per K step
-          umma_f16_ss(tm_PV + buf * FA_D, dP + TILE_STEP * (k >> 2) + 2 * (k & 3), dV + 128 * k, idesc_pv,
-                      k > 0 ? 1u : 0u);
+        for (int sl = 0; sl < (pend_b ? 2 : 1); ++sl) {
+          mbar_wait(&p_full[sl], n_pv[sl] & 1);
+          tc_fence_after();
+          const uint32_t tO = tmem_base + FA_TM_O + sl * 64, tP = tmem_base + FA_TM_P + sl * 64;
+          for (int k = 0; k < ksteps_pv; ++k)   // 16 keys per step: 8 packed columns of P, 16 rows (128 B each) of V
+            umma_f16_ts(tO, tP + 8 * k, dV + 128 * k, idesc_pv, (pend_j > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&pv_done[sl]);
+          ++n_pv[sl];
         }
-        umma_commit(&pv_full[buf]);
         umma_commit(&kv_empty[st]);
       };
       int g = 0, it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const FaTile t = fa_decode(p, tile);
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+        const FaItem t = fa_decode(p, item);
         const int qb = it & 1;
-        const uint64_t dQ = dQ0 + TILE_STEP * qb;
         mbar_wait(&q_full[qb], (uint32_t)((it >> 1) & 1));
         for (int j = 0; j < t.nblk; ++j, ++g) {
-          const int st = g % FA_STAGES, buf = g & 1;
+          const int st = g % FA_STAGES;
           mbar_wait(&k_full[st], (uint32_t)((g / FA_STAGES) & 1));
-          mbar_wait(&s_empty[buf], (uint32_t)(((g >> 1) & 1) ^ 1));
-          tc_fence_after();
           const uint64_t dK = dK0 + TILE_STEP * st;
+          for (int sl = 0; sl < (t.has_b ? 2 : 1); ++sl) {
+            mbar_wait(&s_free[sl], (n_s[sl] & 1) ^ 1);
+            tc_fence_after();
+            const uint64_t dQ = dQ0 + TILE_STEP * (qb * 2 + sl);
 #pragma unroll
-          for (int k = 0; k < FA_D / 16; ++k)
-            umma_f16_ss(tm_S + buf * 128, dQ + 2 * k, dK + 2 * k, idesc_s, k > 0 ? 1u : 0u);
-          umma_commit(&s_full[buf]);
-          if (j == t.nblk - 1) umma_commit(&q_empty[qb]);   // every S MMA reading this Q tile has retired
-          if (g > 0) issue_pv(g - 1);
+            for (int k = 0; k < FA_D / 16; ++k)
+              umma_f16_ss(tmem_base + FA_TM_S + sl * 128, dQ + 2 * k, dK + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+            umma_commit(&s_full[sl]);
+            ++n_s[sl];
+          }
+          if (j == t.nblk - 1) umma_commit(&q_empty[qb]);   // every S MMA reading this Q pair has retired
+          if (pend) issue_pv();
+          pend = true; pend_b = t.has_b; pend_g = g; pend_j = j;
         }
       }
-      if (g > 0) issue_pv(g - 1);
+      if (pend) issue_pv();
     }
     __syncwarp();
   } else {
-    // ===================== softmax / output warps =====================
-    // Two threads per query row: warps w and w+4 share a TMEM lane quarter; the first takes the even 16-column
-    // chunks of S and output channels [0,32), the second the odd chunks and channels [32,64). Each reads its S
-    // values from TMEM once (registers), the pair agrees on the running row maximum through shared memory (one
-    // 64-thread named barrier per block), row sums are combined once per tile.
-    const int sw_id = warp - 2;
-    const int lane_grp = warp & 3;
-    const int half = sw_id >> 2;
+    // ===================== softmax groups: warps 2-5 own tile A, warps 6-9 tile B; thread == query row ==========
+    const int sl = (warp - 2) >> 2;
+    const int lane_grp = warp & 3;                                  // TMEM lane quarter this warp may access
     const int row = lane_grp * 32 + lane;
     const uint32_t lane_addr = uint32_t(lane_grp * 32) << 16;
-    float* xch = reinterpret_cast<float*>(smem + FA_SMEM_XCH);      // [buf][half][row]
-    float* xch_l = xch + 2 * 2 * 128;                               // [half][row]
-    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
-    float O[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) O[i] = 0.f;
+    const uint32_t tS = tmem_base + lane_addr + FA_TM_S + sl * 128;
+    const uint32_t tP = tmem_base + lane_addr + FA_TM_P + sl * 64;
+    const uint32_t tO = tmem_base + lane_addr + FA_TM_O + sl * 64;
     const int nchunk = NCH > 0 ? NCH : p.kv_n / 16;
     const float c = p.scale_log2;
-    const uint32_t bar_id = 1 + lane_grp;
+    const f32x2 c2 = f2_splat(c);
 
-    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory"); };
-
-    auto consume_pv = [&](int i, float alpha) {
-      const int buf = i & 1;
-      mbar_wait(&pv_full[buf], (uint32_t)((i >> 1) & 1));
-      tc_fence_after();
-      uint32_t v[32];
-      tmem_ld_32x32(tm_PV + lane_addr + buf * FA_D + half * 32, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int t = 0; t < 32; ++t) O[t] = O[t] * alpha + __uint_as_float(v[t]);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&pv_empty[buf]);
-    };
-
-    // combine the pair's partial row sums, normalise and store this thread's 32 channels; then clear O
-    auto finish_tile = [&](const FaTile& t, float l_part) {
-      pair_sync();
-      xch_l[half * 128 + row] = l_part;
-      pair_sync();
-      const float l_tot = l_part + xch_l[(half ^ 1) * 128 + row];
+    // normalise O_t by the row sum and store the 64 channels of this thread's query row (bf16)
+    auto epilogue = [&](int ti, int head, int view, int frame, float l_tot) {
       const int yy = row / p.qw, xx = row - yy * p.qw;
-      const int x = t.x0 + xx, y = t.y0 + yy;
-      if (row < p.qw * p.qh && x < p.W && y < p.H) {
-        const float inv = 1.f / l_tot;
-        const long long token = (((long long)t.frame * p.H + y) * p.V + t.view) * p.W + x;
-        __nv_bfloat16* dst = p.out + token * p.out_ld + t.head * FA_D + half * 32;
+      const int x = (ti % p.tiles_x) * p.qw + xx, y = (ti / p.tiles_x) * p.qh + yy;
+      const bool ok = row < p.qw * p.qh && x < p.W && y < p.H;
+      const float inv = 1.f / l_tot;
+      const long long token = (((long long)frame * p.H + y) * p.V + view) * p.W + x;
+      __nv_bfloat16* dst = p.out + token * p.out_ld + head * FA_D;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          *reinterpret_cast<uint4*>(dst + i * 8) =
-              make_uint4(pack_bf16x2(O[i * 8 + 0] * inv, O[i * 8 + 1] * inv), pack_bf16x2(O[i * 8 + 2] * inv, O[i * 8 + 3] * inv),
-                         pack_bf16x2(O[i * 8 + 4] * inv, O[i * 8 + 5] * inv), pack_bf16x2(O[i * 8 + 6] * inv, O[i * 8 + 7] * inv));
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t o[32];
+        tmem_ld_32x32(tO + hh * 32, o);
+        tmem_ld_wait();
+        if (ok) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            *reinterpret_cast<uint4*>(dst + hh * 32 + i * 8) = make_uint4(
+                pack_bf16x2(__uint_as_float(o[i * 8 + 0]) * inv, __uint_as_float(o[i * 8 + 1]) * inv),
+                pack_bf16x2(__uint_as_float(o[i * 8 + 2]) * inv, __uint_as_float(o[i * 8 + 3]) * inv),
+                pack_bf16x2(__uint_as_float(o[i * 8 + 4]) * inv, __uint_as_float(o[i * 8 + 5]) * inv),
+                pack_bf16x2(__uint_as_float(o[i * 8 + 6]) * inv, __uint_as_float(o[i * 8 + 7]) * inv));
+          }
         }
       }
-#pragma unroll
-      for (int i = 0; i < 32; ++i) O[i] = 0.f;
     };
 
-    int g = 0;
-    FaTile prev;
-    prev.x0 = prev.y0 = prev.head = prev.view = prev.frame = prev.nblk = 0;
-    float l_prev = 0.f;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const FaTile t = fa_decode(p, tile);
-      l_prev = l_run;
-      m_run = -INFINITY;
-      l_run = 0.f;
-      for (int j = 0; j < t.nblk; ++j, ++g) {
-        const int buf = g & 1;
-        mbar_wait(&s_full[buf], (uint32_t)((g >> 1) & 1));
+    uint32_t n = 0;                  // blocks this group has processed (phase of s_full / pv_done)
+    bool have_prev = false;
+    int prev_ti = 0, prev_head = 0, prev_view = 0, prev_frame = 0;
+    float l_prev = 1.f;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      const FaItem t = fa_decode(p, item);
+      if (sl == 1 && !t.has_b) continue;
+      float m_run = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < t.nblk; ++j, ++n) {
+        mbar_wait(&s_full[sl], n & 1);
         tc_fence_after();
-        const uint32_t tS = tm_S + lane_addr + buf * 128;
-        // my chunks of S -> registers (single TMEM pass)
-        uint32_t sv[4][16];
+        uint32_t sv[8][16];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int ch = half + 2 * q;
-          if (ch < nchunk) tmem_ld_32x16(tS + ch * 16, sv[q]);
-        }
+        for (int ch = 0; ch < 8; ++ch)
+          if (ch < nchunk) tmem_ld_32x16(tS + ch * 16, sv[ch]);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[buf]);  // S buffer may be overwritten by the MMA of block g+2
-        // four independent max chains per chunk (a single 56-long dependent chain would cost ~4 cycles per element)
+        if (lane == 0) mbar_arrive(&s_free[sl]);      // the tensor core may overwrite S_t with the next block
+        // row maximum: four independent chains per chunk
         float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int ch = half + 2 * q;
+        for (int ch = 0; ch < 8; ++ch) {
           if (ch < nchunk) {
 #pragma unroll
             for (int tt = 0; tt < 16; ++tt)
-              if (!MASK || ch * 16 + tt < p.kv_rows) mx4[tt & 3] = fmaxf(mx4[tt & 3], __uint_as_float(sv[q][tt]));
+              if (!MASK || ch * 16 + tt < p.kv_rows) mx4[tt & 3] = fmaxf(mx4[tt & 3], __uint_as_float(sv[ch][tt]));
           }
         }
-        float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-        float* xb = xch + buf * 256;
-        xb[half * 128 + row] = mx;
-        pair_sync();
-        mx = fmaxf(mx, xb[(half ^ 1) * 128 + row]);
-        const float m_new = fmaxf(m_run, mx * c);
-        const float alpha = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run - m_new);
-        float rs4[4] = {0.f, 0.f, 0.f, 0.f};
-        uint8_t* sP = smem + FA_SMEM_P + buf * 2 * FA_TILE_BYTES;
+        const float m_new = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * c;
+        const bool upd = m_new > m_run + FA_LAZY_LOG2;               // always true for the first block (m_run = -inf)
+        const float alpha = upd ? ex2_approx(m_run - m_new) : 1.f;   // first block: exp2(-inf) = 0
+        if (upd) m_run = m_new;
+        const bool need = (j > 0) && __any_sync(0xffffffffu, upd);
+        const f32x2 nm2 = f2_splat(-m_run);
+        f32x2 rs2[2] = {0ull, 0ull};
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int ch = half + 2 * q;
+        for (int ch = 0; ch < 8; ++ch) {
           if (ch < nchunk) {
-            float e[16];
 #pragma unroll
-            for (int tt = 0; tt < 16; ++tt) {
-              const float pv = ex2_approx(__uint_as_float(sv[q][tt]) * c - m_new);
-              e[tt] = (!MASK || ch * 16 + tt < p.kv_rows) ? pv : 0.f;
-              rs4[tt & 3] += e[tt];
+            for (int tt = 0; tt < 8; ++tt) {
+              const f32x2 xs = f2_fma(f2_pack(__uint_as_float(sv[ch][2 * tt]), __uint_as_float(sv[ch][2 * tt + 1])), c2, nm2);
+              float x0, x1;
+              f2_unpack(xs, x0, x1);
+              float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
+              if (MASK) {
+                if (ch * 16 + 2 * tt >= p.kv_rows) e0 = 0.f;
+                if (ch * 16 + 2 * tt + 1 >= p.kv_rows) e1 = 0.f;
+              }
+              rs2[tt & 1] = f2_add(rs2[tt & 1], f2_pack(e0, e1));
+              sv[ch][tt] = pack_bf16x2(e0, e1);        // packed P overwrites the (dead) first half of the chunk
             }
-            // 16 keys = 2 chunks of 16 B inside atom (ch/4); chunk index within the 128 B row = (ch%4)*2 + {0,1}
-            uint8_t* atom = sP + (ch >> 2) * FA_TILE_BYTES + row * 128;
-            const int c0 = (ch & 3) * 2;
-            *reinterpret_cast<uint4*>(atom + ((c0 ^ (row & 7)) << 4)) =
-                make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
-            *reinterpret_cast<uint4*>(atom + (((c0 + 1) ^ (row & 7)) << 4)) =
-                make_uint4(pack_bf16x2(e[8], e[9]), pack_bf16x2(e[10], e[11]), pack_bf16x2(e[12], e[13]), pack_bf16x2(e[14], e[15]));
           }
         }
-        fence_proxy_async_smem();                   // every writer publishes its P stores to the async proxy ...
-        __syncwarp();                               // ... before the warp's single arrive
-        if (lane == 0) mbar_arrive(&p_full[buf]);
-        l_run = l_run * alpha + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
-        m_run = m_new;
-        if (g > 0) {
-          consume_pv(g - 1, alpha_prev);            // block g-1 may be the last block of the previous tile
-          if (j == 0) finish_tile(prev, l_prev);
+        {
+          float a0, a1;
+          f2_unpack(f2_add(rs2[0], rs2[1]), a0, a1);
+          l_run = l_run * alpha + (a0 + a1);
         }
-        alpha_prev = alpha;
+        // P_t / O_t may only be touched once the previous PV of this tile slot has retired
+        mbar_wait(&pv_done[sl], (n & 1) ^ 1);
+        tc_fence_after();
+        if (j == 0) {
+          if (have_prev) epilogue(prev_ti, prev_head, prev_view, prev_frame, l_prev);
+        } else if (need) {
+          // the reference maximum of some row moved: rescale the accumulator in place (alpha = 1 for the other rows)
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t o[32];
+            tmem_ld_32x32(tO + hh * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32(tO + hh * 32, o);
+          }
+        }
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          if (ch < nchunk) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int tt = 0; tt < 8; ++tt) pk[tt] = sv[ch][tt];
+            tmem_st_32x8(tP + ch * 8, pk);
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[sl]);
       }
-      prev = t;
+      have_prev = true;
+      prev_ti = t.t0 + sl; prev_head = t.head; prev_view = t.view; prev_frame = t.frame;
+      l_prev = l_run;
     }
-    if (g > 0) {
-      consume_pv(g - 1, alpha_prev);
-      finish_tile(prev, l_run);
+    if (have_prev) {
+      mbar_wait(&pv_done[sl], (n & 1) ^ 1);
+      tc_fence_after();
+      epilogue(prev_ti, prev_head, prev_view, prev_frame, l_prev);
     }
   }
 
@@ -433,10 +441,12 @@ extern "C" int pn_attention(const pn_attn_args* a, void* stream_v) {
       PN_CHECK_CUDA(cudaFuncSetAttribute(fa_kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_TOTAL));
     attr_set = true;
   }
-  const long long tiles = (long long)p.tiles_x * p.tiles_y * a->heads * a->V * a->F;
-  PN_REQUIRE(tiles > 0 && tiles < (1ll << 31), "pn_attention: too many query tiles");
-  p.total_tiles = (int)tiles;
-  const int grid = tiles < sm_count() ? (int)tiles : sm_count();
+  p.tiles_per_group = p.tiles_x * p.tiles_y;
+  p.pairs = (p.tiles_per_group + 1) / 2;
+  const long long items = (long long)p.pairs * a->heads * a->V * a->F;
+  PN_REQUIRE(items > 0 && items < (1ll << 31), "pn_attention: too many query tiles");
+  p.total_items = (int)items;
+  const int grid = items < sm_count() ? (int)items : sm_count();
   const int nch = p.kv_n / 16;
   const int slot = nch == 8 ? 4 : nch == 7 ? 3 : nch == 5 ? 2 : nch == 2 ? 1 : 0;
   fa_kernels[(p.kv_rows < p.kv_n ? 5 : 0) + slot]<<<grid, FA_THREADS, FA_SMEM_TOTAL, reinterpret_cast<cudaStream_t>(stream_v)>>>(p);
