@@ -54,6 +54,7 @@ struct FaParams {
   int kv_frame_div;            // kv frame = q frame / kv_frame_div
   int total_items;
   float scale_log2;            // softmax scale * log2(e)
+  int debug;                   // PN_ATTN_DEBUG (timing experiments): 1 = no softmax math, 2 = no MMA issue
   __nv_bfloat16* out;
   long long out_ld;            // token stride of out (elements)
 };
@@ -129,8 +130,8 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (warp-wide loop, TMA issue under elect.sync) =====================
+    {
       const uint32_t q_bytes = (uint32_t)(p.qw * p.qh) * 128u;
       const uint32_t kv_bytes = (uint32_t)p.kv_rows * 128u;
       int g = 0, it = 0;
@@ -138,31 +139,36 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
         const FaItem t = fa_decode(p, item);
         const int qb = it & 1;
         mbar_wait(&q_empty[qb], (uint32_t)(((it >> 1) & 1) ^ 1));
-        mbar_arrive_expect_tx(&q_full[qb], t.has_b ? 2 * q_bytes : q_bytes);
-        for (int sl = 0; sl < (t.has_b ? 2 : 1); ++sl) {
-          const int ti = t.t0 + sl;
-          tma_load_5d(smem + FA_SMEM_Q + (qb * 2 + sl) * FA_TILE_BYTES, &p.mapQ, &q_full[qb], t.head * FA_D,
-                      (ti % p.tiles_x) * p.qw, t.view, (ti / p.tiles_x) * p.qh, t.frame);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&q_full[qb], t.has_b ? 2 * q_bytes : q_bytes);
+          for (int sl = 0; sl < (t.has_b ? 2 : 1); ++sl) {
+            const int ti = t.t0 + sl;
+            tma_load_5d(smem + FA_SMEM_Q + (qb * 2 + sl) * FA_TILE_BYTES, &p.mapQ, &q_full[qb], t.head * FA_D,
+                        (ti % p.tiles_x) * p.qw, t.view, (ti / p.tiles_x) * p.qh, t.frame);
+          }
         }
         const int kv_frame = t.frame / p.kv_frame_div;
+        int vi = 0, yb = 0;
         for (int j = 0; j < t.nblk; ++j, ++g) {
           const int st = g % FA_STAGES;
-          const int vi = j / p.kv_yblocks, yb = j - vi * p.kv_yblocks;
           const int kvv = p.kv_views[t.view][vi];
           mbar_wait(&kv_empty[st], (uint32_t)(((g / FA_STAGES) & 1) ^ 1));
-          mbar_arrive_expect_tx(&k_full[st], kv_bytes);
-          tma_load_5d(smem + FA_SMEM_K + st * FA_TILE_BYTES, &p.mapK, &k_full[st], t.head * FA_D, 0, kvv, yb * p.kh, kv_frame);
-          mbar_arrive_expect_tx(&v_full[st], kv_bytes);
-          tma_load_5d(smem + FA_SMEM_V + st * FA_TILE_BYTES, &p.mapV, &v_full[st], t.head * FA_D, 0, kvv, yb * p.kh, kv_frame);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&k_full[st], kv_bytes);
+            tma_load_5d(smem + FA_SMEM_K + st * FA_TILE_BYTES, &p.mapK, &k_full[st], t.head * FA_D, 0, kvv, yb * p.kh, kv_frame);
+            mbar_arrive_expect_tx(&v_full[st], kv_bytes);
+            tma_load_5d(smem + FA_SMEM_V + st * FA_TILE_BYTES, &p.mapV, &v_full[st], t.head * FA_D, 0, kvv, yb * p.kh, kv_frame);
+          }
+          if (++yb == p.kv_yblocks) { yb = 0; ++vi; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== UMMA issuer (one thread runs the whole loop; descriptors advance by integer adds) ====
-    if (lane == 0) {
+    // ===================== UMMA issuer (warp-wide loop; MMAs and commits under elect.sync, descriptors = base + k) ====
+    {
       const uint32_t idesc_s = umma_idesc_bf16(128, p.kv_n, 0, 0);      // S = Q K^T : both K-major
       const uint32_t idesc_pv = umma_idesc_bf16(128, FA_D, 0, 1);       // PV: A = P (tensor memory), B = V MN-major
-      const int ksteps_pv = p.kv_n / 16;
+      const int ksteps_pv = NCH > 0 ? NCH : p.kv_n / 16;
       const uint64_t dQ0 = umma_smem_desc(smem_u32(smem + FA_SMEM_Q), 16, 1024);
       const uint64_t dK0 = umma_smem_desc(smem_u32(smem + FA_SMEM_K), 16, 1024);
       const uint64_t dV0 = umma_smem_desc(smem_u32(smem + FA_SMEM_V), 1024, 1024);
@@ -175,16 +181,22 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
         const int st = pend_g % FA_STAGES;
         mbar_wait(&v_full[st], (uint32_t)((pend_g / FA_STAGES) & 1));
         const uint64_t dV = dV0 + TILE_STEP * st;
-        for (int sl = 0; sl < (pend_b ? 2 : 1); ++sl) {
-          mbar_wait(&p_full[sl], n_pv[sl] & 1);
-          tc_fence_after();
-          const uint32_t tO = tmem_base + FA_TM_O + sl * 64, tP = tmem_base + FA_TM_P + sl * 64;
-          for (int k = 0; k < ksteps_pv; ++k)   // 16 keys per step: 8 packed columns of P, 16 rows (128 B each) of V
-            umma_f16_ts(tO, tP + 8 * k, dV + 128 * k, idesc_pv, (pend_j > 0 || k > 0) ? 1u : 0u);
-          umma_commit(&pv_done[sl]);
-          ++n_pv[sl];
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          if (sl == 0 || pend_b) {
+            mbar_wait(&p_full[sl], n_pv[sl] & 1);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t tO = tmem_base + FA_TM_O + sl * 64, tP = tmem_base + FA_TM_P + sl * 64;
+#pragma unroll
+              for (int k = 0; k < 8; ++k)   // 16 keys per step: 8 packed columns of P, 16 rows (128 B each) of V
+                if (k < ksteps_pv && p.debug != 2) umma_f16_ts(tO, tP + 8 * k, dV + 128 * k, idesc_pv, (pend_j > 0 || k > 0) ? 1u : 0u);
+              umma_commit(&pv_done[sl]);
+              if (sl == 1 || !pend_b) umma_commit(&kv_empty[st]);
+            }
+            ++n_pv[sl];
+          }
         }
-        umma_commit(&kv_empty[st]);
       };
       int g = 0, it = 0;
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
@@ -195,24 +207,31 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
           const int st = g % FA_STAGES;
           mbar_wait(&k_full[st], (uint32_t)((g / FA_STAGES) & 1));
           const uint64_t dK = dK0 + TILE_STEP * st;
-          for (int sl = 0; sl < (t.has_b ? 2 : 1); ++sl) {
-            mbar_wait(&s_free[sl], (n_s[sl] & 1) ^ 1);
-            tc_fence_after();
-            const uint64_t dQ = dQ0 + TILE_STEP * (qb * 2 + sl);
 #pragma unroll
-            for (int k = 0; k < FA_D / 16; ++k)
-              umma_f16_ss(tmem_base + FA_TM_S + sl * 128, dQ + 2 * k, dK + 2 * k, idesc_s, k > 0 ? 1u : 0u);
-            umma_commit(&s_full[sl]);
-            ++n_s[sl];
+          for (int sl = 0; sl < 2; ++sl) {
+            if (sl == 0 || t.has_b) {
+              mbar_wait(&s_free[sl], (n_s[sl] & 1) ^ 1);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint64_t dQ = dQ0 + TILE_STEP * (qb * 2 + sl);
+                if (p.debug != 2) {
+#pragma unroll
+                  for (int k = 0; k < FA_D / 16; ++k)
+                    umma_f16_ss(tmem_base + FA_TM_S + sl * 128, dQ + 2 * k, dK + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+                }
+                umma_commit(&s_full[sl]);
+                // every S MMA reading this Q pair has retired
+                if (j == t.nblk - 1 && (sl == 1 || !t.has_b)) umma_commit(&q_empty[qb]);
+              }
+              ++n_s[sl];
+            }
           }
-          if (j == t.nblk - 1) umma_commit(&q_empty[qb]);   // every S MMA reading this Q pair has retired
           if (pend) issue_pv();
           pend = true; pend_b = t.has_b; pend_g = g; pend_j = j;
         }
       }
       if (pend) issue_pv();
     }
-    __syncwarp();
   } else {
     // ===================== softmax groups: warps 2-5 own tile A, warps 6-9 tile B; thread == query row ==========
     const int sl = (warp - 2) >> 2;
@@ -252,6 +271,10 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
       }
     };
 
+    // The exp2 phase saturates the MUFU of all four schedulers; the two groups take turns in it (named barriers
+    // 1 = "A may go", 2 = "B may go"), so one group's TMEM traffic, maxima and barrier waits hide behind the other's
+    // exponentials instead of the two running in lock step. Group B hands A the first turn.
+    if (sl == 1) named_bar_arrive(1, 256);
     uint32_t n = 0;                  // blocks this group has processed (phase of s_full / pv_done)
     bool have_prev = false;
     int prev_ti = 0, prev_head = 0, prev_view = 0, prev_frame = 0;
@@ -271,6 +294,16 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_free[sl]);      // the tensor core may overwrite S_t with the next block
+        if (p.debug == 1) {
+          mbar_wait(&pv_done[sl], (n & 1) ^ 1);
+          tc_fence_after();
+          if (j == 0 && have_prev) epilogue(prev_ti, prev_head, prev_view, prev_frame, l_prev);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[sl]);
+          l_run = 1.f;
+          continue;
+        }
         // row maximum: four independent chains per chunk
         float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
@@ -288,6 +321,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
         const bool need = (j > 0) && __any_sync(0xffffffffu, upd);
         const f32x2 nm2 = f2_splat(-m_run);
         f32x2 rs2[2] = {0ull, 0ull};
+        if (t.has_b) named_bar_sync(1 + sl, 256);
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) {
           if (ch < nchunk) {
@@ -296,7 +330,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
               const f32x2 xs = f2_fma(f2_pack(__uint_as_float(sv[ch][2 * tt]), __uint_as_float(sv[ch][2 * tt + 1])), c2, nm2);
               float x0, x1;
               f2_unpack(xs, x0, x1);
-              float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
+              float e0 = ex2_approx_ordered(x0), e1 = ex2_approx_ordered(x1);
               if (MASK) {
                 if (ch * 16 + 2 * tt >= p.kv_rows) e0 = 0.f;
                 if (ch * 16 + 2 * tt + 1 >= p.kv_rows) e1 = 0.f;
@@ -309,7 +343,11 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
         {
           float a0, a1;
           f2_unpack(f2_add(rs2[0], rs2[1]), a0, a1);
-          l_run = l_run * alpha + (a0 + a1);
+          const float rs = a0 + a1;
+          // the hand-over must not be scheduled ahead of the exponentials it stands for: its thread count is made to
+          // depend (vacuously — a row sum is never this NaN pattern) on the sum of all of them
+          if (t.has_b) named_bar_arrive(2 - sl, 256u + (__float_as_uint(rs) == 0x7fc0beefu ? 32u : 0u));
+          l_run = l_run * alpha + rs;
         }
         // P_t / O_t may only be touched once the previous PV of this tile slot has retired
         mbar_wait(&pv_done[sl], (n & 1) ^ 1);
@@ -346,6 +384,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
       prev_ti = t.t0 + sl; prev_head = t.head; prev_view = t.view; prev_frame = t.frame;
       l_prev = l_run;
     }
+    if (sl == 0) named_bar_sync(1, 256);          // consume the turn that is still outstanding
     if (have_prev) {
       mbar_wait(&pv_done[sl], (n & 1) ^ 1);
       tc_fence_after();
@@ -412,6 +451,11 @@ extern "C" int pn_attention(const pn_attn_args* a, void* stream_v) {
   }
   p.kv_frame_div = a->kv_frame_div;
   p.scale_log2 = a->scale * 1.4426950408889634f;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = std::getenv("PN_ATTN_DEBUG"); dbg = e ? std::atoi(e) : 0; }
+    p.debug = dbg;
+  }
   p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
   p.out_ld = a->out_ld;
 

@@ -160,21 +160,27 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
+  // Producer and issuer loops are executed by all 32 lanes of their warp with the asynchronous instructions under an
+  // elect.sync predicate: ptxas then emits the TMA / UMMA instructions straight from uniform registers. (Issued from
+  // a `lane == 0` branch every one of them is wrapped in an elect/vote loop, and the single-thread instruction stream
+  // — not the tensor core — set the pace: ~145 cycles per UMMA whatever its N, measured with tools/mma_probe.py
+  // against 64 cycles for N = 128 in tools/ubench/umma_rate.cu.)
   if (warp == 0 && MODE == 6) {
     // ===================== MODE 6 producer: one haloed A tile per 64-channel chunk, nine weight tiles per chunk ==========
-    if (lane == 0) {
-      uint8_t* ringA = stage_base;
-      uint8_t* ringB = stage_base + S::HALO_STAGES * S::A_HALO_BYTES;
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
-      for (int tile = unit; tile < num_tiles; tile += num_units) {
-        const int tcol = tile % p.tiles_col;
-        int tm = (tile / p.tiles_col) * NCTA + (int)cta_rank;
-        const int twi = tm % p.tiles_w; tm /= p.tiles_w;
-        const int thi = tm % p.tiles_h; tm /= p.tiles_h;
-        const int x0 = twi * p.tw, y0 = thi * p.th, n0 = tm * p.tn;
-        for (int kc = 0; kc < p.kc_per_tap; ++kc) {
-          mbar_wait(&a_empty[sa], pa ^ 1);
+    uint8_t* ringA = stage_base;
+    uint8_t* ringB = stage_base + S::HALO_STAGES * S::A_HALO_BYTES;
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    for (int tile = unit; tile < num_tiles; tile += num_units) {
+      const int tcol = tile % p.tiles_col;
+      int tm = (tile / p.tiles_col) * NCTA + (int)cta_rank;
+      const int twi = tm % p.tiles_w; tm /= p.tiles_w;
+      const int thi = tm % p.tiles_h; tm /= p.tiles_h;
+      const int x0 = twi * p.tw, y0 = thi * p.th, n0 = tm * p.tn;
+      const int bn0 = tcol * BN + (NCTA == 2 ? (int)cta_rank * (BN / 2) : 0);
+      for (int kc = 0; kc < p.kc_per_tap; ++kc) {
+        mbar_wait(&a_empty[sa], pa ^ 1);
+        if (elect_one()) {
           if (NCTA == 2) {
             if (cta_rank == 0) mbar_arrive_expect_tx(&a_full[sa], 2 * S::A_HALO_TX);
             tma_load_4d_2sm(ringA + sa * S::A_HALO_BYTES, &p.mapA, &a_full[sa], kc * BK, x0 - 1, y0 - 1, n0);
@@ -182,26 +188,28 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
             mbar_arrive_expect_tx(&a_full[sa], S::A_HALO_TX);
             tma_load_4d(ringA + sa * S::A_HALO_BYTES, &p.mapA, &a_full[sa], kc * BK, x0 - 1, y0 - 1, n0);
           }
-          if (++sa == S::HALO_STAGES) { sa = 0; pa ^= 1; }
-          for (int tap = 0; tap < 9; ++tap) {
-            mbar_wait(&empty_bar[sb], pb ^ 1);
+        }
+        if (++sa == S::HALO_STAGES) { sa = 0; pa ^= 1; }
+        int kcol = kc * BK;                               // weight column of (tap 0, chunk kc); one tap = C columns
+        for (int tap = 0; tap < 9; ++tap, kcol += p.kc_per_tap * BK) {
+          mbar_wait(&empty_bar[sb], pb ^ 1);
+          if (elect_one()) {
             uint8_t* sB = ringB + sb * S::B_BYTES;
-            const int kcol = (tap * p.kc_per_tap + kc) * BK;
             if (NCTA == 2) {
               if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[sb], 2 * S::B_BYTES);
-              tma_load_2d_2sm(sB, &p.mapB, &full_bar[sb], kcol, tcol * BN + (int)cta_rank * (BN / 2));
+              tma_load_2d_2sm(sB, &p.mapB, &full_bar[sb], kcol, bn0);
             } else {
               mbar_arrive_expect_tx(&full_bar[sb], S::B_BYTES);
-              tma_load_2d(sB, &p.mapB, &full_bar[sb], kcol, tcol * BN);
+              tma_load_2d(sB, &p.mapB, &full_bar[sb], kcol, bn0);
             }
-            if (++sb == STAGES) { sb = 0; pb ^= 1; }
           }
+          if (++sb == STAGES) { sb = 0; pb ^= 1; }
         }
       }
     }
   } else if (warp == 1 && MODE == 6) {
     // ===================== MODE 6 UMMA issuer: tap (dy,dx) = the A view shifted by dy*(tw+2)+dx rows ==========
-    if (cta_rank == 0 && lane == 0) {
+    if (cta_rank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM * NCTA, BN, 0, 0);
       const uint32_t ringA = smem_u32(stage_base);
       const uint32_t ringB = ringA + S::HALO_STAGES * S::A_HALO_BYTES;
@@ -222,23 +230,25 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(&full_bar[sb], pb);
             tc_fence_after();
-            const uint64_t da = da_tile + (uint64_t)(((tap / 3) * 10 + (tap % 3)) * 8);    // rows * 128 B / 16
-            const uint64_t db = descB0 + (uint64_t)(S::B_BYTES >> 4) * sb;
+            if (elect_one()) {
+              const uint64_t da = da_tile + (uint64_t)(((tap / 3) * 10 + (tap % 3)) * 8);    // rows * 128 B / 16
+              const uint64_t db = descB0 + (uint64_t)(S::B_BYTES >> 4) * sb;
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              const uint32_t accum = (kc > 0 || tap > 0 || k > 0) ? 1u : 0u;
-              if (NCTA == 2) umma_f16_ss_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
-              else umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
-            }
-            const bool last = (kc == p.kc_per_tap - 1) && (tap == 8);
-            if (NCTA == 2) {
-              umma_commit_2sm(&empty_bar[sb], 3);
-              if (tap == 8) umma_commit_2sm(&a_empty[sa], 3);
-              if (last) umma_commit_2sm(&tmem_full[acc], 3);
-            } else {
-              umma_commit(&empty_bar[sb]);
-              if (tap == 8) umma_commit(&a_empty[sa]);
-              if (last) umma_commit(&tmem_full[acc]);
+              for (int k = 0; k < BK / 16; ++k) {
+                const uint32_t accum = (kc > 0 || tap > 0 || k > 0) ? 1u : 0u;
+                if (NCTA == 2) umma_f16_ss_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
+                else umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
+              }
+              const bool last = (kc == p.kc_per_tap - 1) && (tap == 8);
+              if (NCTA == 2) {
+                umma_commit_2sm(&empty_bar[sb], 3);
+                if (tap == 8) umma_commit_2sm(&a_empty[sa], 3);
+                if (last) umma_commit_2sm(&tmem_full[acc], 3);
+              } else {
+                umma_commit(&empty_bar[sb]);
+                if (tap == 8) umma_commit(&a_empty[sa]);
+                if (last) umma_commit(&tmem_full[acc]);
+              }
             }
             if (++sb == STAGES) { sb = 0; pb ^= 1; }
           }
@@ -249,44 +259,49 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
     }
   } else if (warp == 0) {
     // ===================== TMA producer (every CTA loads its own A rows and its share of B) =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = unit; tile < num_tiles; tile += num_units) {
-        const int tcol = tile % p.tiles_col;
-        int tm = (tile / p.tiles_col) * NCTA + (int)cta_rank;
-        const int twi = tm % p.tiles_w; tm /= p.tiles_w;
-        const int thi = tm % p.tiles_h; tm /= p.tiles_h;
-        const int tni = tm;                       // >= tiles_n for the odd tail of a pair: fully OOB -> zero fill
-        const int x0 = twi * p.tw, y0 = thi * p.th, n0 = tni * p.tn;
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
-          const int tap = kb / p.kc_per_tap;
-          const int kc = kb - tap * p.kc_per_tap;
-          const int dy = tap / p.taps_w - p.pad_h;
-          const int dx = tap % p.taps_w - p.pad_w;
-          if (p.debug == 1 && (tile != unit || kb >= STAGES)) continue;   // experiment: the ring is filled once, never again
+    int stage = 0;
+    uint32_t phase = 0;
+    bool first = true;
+    for (int tile = unit; tile < num_tiles; tile += num_units) {
+      const int tcol = tile % p.tiles_col;
+      int tm = (tile / p.tiles_col) * NCTA + (int)cta_rank;
+      const int twi = tm % p.tiles_w; tm /= p.tiles_w;
+      const int thi = tm % p.tiles_h; tm /= p.tiles_h;
+      const int tni = tm;                       // >= tiles_n for the odd tail of a pair: fully OOB -> zero fill
+      const int x0 = twi * p.tw, y0 = thi * p.th, n0 = tni * p.tn;
+      const int bn0 = tcol * BN + (NCTA == 2 ? (int)cta_rank * (BN / 2) : 0);
+      int kc = 0, dx = -p.pad_w, dy = -p.pad_h;   // k-block -> (tap row, tap column, channel chunk), kept incrementally
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        if (!(p.debug == 1 && !(first && kb < STAGES))) {   // experiment 1: the ring is filled once, never again
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sA = stage_base + stage * S::STAGE_BYTES;
-          uint8_t* sB = sA + S::A_BYTES;
-          if (NCTA == 2) {
-            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);   // bytes of both CTAs
-            tma_load_4d_2sm(sA, &p.mapA, &full_bar[stage], kc * BK, x0 + dx, y0 + dy, n0);
-            tma_load_2d_2sm(sB, &p.mapB, &full_bar[stage], kb * BK, tcol * BN + (int)cta_rank * (BN / 2));
-          } else {
-            mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
-            tma_load_4d(sA, &p.mapA, &full_bar[stage], kc * BK, x0 + dx, y0 + dy, n0);
-            tma_load_2d(sB, &p.mapB, &full_bar[stage], kb * BK, tcol * BN);
+          if (elect_one()) {
+            uint8_t* sA = stage_base + stage * S::STAGE_BYTES;
+            uint8_t* sB = sA + S::A_BYTES;
+            if (NCTA == 2) {
+              if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);   // bytes of both CTAs
+              tma_load_4d_2sm(sA, &p.mapA, &full_bar[stage], kc * BK, x0 + dx, y0 + dy, n0);
+              tma_load_2d_2sm(sB, &p.mapB, &full_bar[stage], kb * BK, bn0);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+              tma_load_4d(sA, &p.mapA, &full_bar[stage], kc * BK, x0 + dx, y0 + dy, n0);
+              tma_load_2d(sB, &p.mapB, &full_bar[stage], kb * BK, bn0);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        if (++kc == p.kc_per_tap) {
+          kc = 0;
+          if (++dx > p.taps_w - 1 - p.pad_w) { dx = -p.pad_w; ++dy; }
+        }
       }
+      first = false;
     }
   } else if (warp == 1) {
-    // ===================== UMMA issuer (leader CTA of a pair only; ONE thread runs the whole loop) =====================
-    // The issue loop is the critical resource of the kernel (measured: ~150 instructions per k-block made every
-    // k-block cost ~650 cycles whatever the tile): descriptors are advanced by integer adds on precomputed 64-bit
-    // bases, no per-iteration election / warp sync, and only lane 0 polls the barriers.
-    if (cta_rank == 0 && lane == 0) {
+    // ===================== UMMA issuer (leader CTA of a pair only) =====================
+    // Kept deliberately plain (runtime ring position, descriptors = uniform base + stage * step + k): in this form ptxas
+    // keeps every operand in uniform registers; unrolling by the ring position made it hoist 8 x STAGES descriptors into
+    // vector registers and pay an R2UR per operand per MMA.
+    if (cta_rank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM * NCTA, BN, 0, 0);
       const uint64_t descA0 = umma_smem_desc(smem_u32(stage_base), 16, 1024);
       const uint64_t descB0 = umma_smem_desc(smem_u32(stage_base) + S::A_BYTES, 16, 1024);
@@ -295,32 +310,36 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      bool first = true;
       for (int tile = unit; tile < num_tiles; tile += num_units) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
-          if (!(p.debug == 1 && (tile != unit || kb >= STAGES))) mbar_wait(&full_bar[stage], phase);
+          if (!(p.debug == 1 && !(first && kb < STAGES))) mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t da = descA0 + STAGE_STEP * stage;
-          const uint64_t db = descB0 + STAGE_STEP * stage;
-          if (p.debug != 2) {
+          if (elect_one()) {
+            const uint64_t da = descA0 + STAGE_STEP * stage;
+            const uint64_t db = descB0 + STAGE_STEP * stage;
+            if (p.debug != 2) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              if (NCTA == 2) umma_f16_ss_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-              else umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < BK / 16; ++k) {
+                if (NCTA == 2) umma_f16_ss_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                else umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              }
             }
-          }
-          // commit: frees the smem slot (in both CTAs) once the MMAs retire; the last one also publishes the tile
-          if (NCTA == 2) {
-            umma_commit_2sm(&empty_bar[stage], 3);
-            if (kb == num_k_blocks - 1) umma_commit_2sm(&tmem_full[acc], 3);
-          } else {
-            umma_commit(&empty_bar[stage]);
-            if (kb == num_k_blocks - 1) umma_commit(&tmem_full[acc]);
+            // commit: frees the smem slot (in both CTAs) once the MMAs retire; the last one also publishes the tile
+            if (NCTA == 2) {
+              umma_commit_2sm(&empty_bar[stage], 3);
+              if (kb == num_k_blocks - 1) umma_commit_2sm(&tmem_full[acc], 3);
+            } else {
+              umma_commit(&empty_bar[stage]);
+              if (kb == num_k_blocks - 1) umma_commit(&tmem_full[acc]);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        first = false;
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -594,7 +613,6 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
                 *reinterpret_cast<uint4*>(out + (long long)grow * p.ldo + no0 + ch * 8) = val;
               }
             }
-            __syncwarp();
           } else if (MODE == 1) {
             // 32 bf16 = 64 B per row, 16 B chunks XOR-swizzled with (row>>1)&3
 #pragma unroll
@@ -627,7 +645,6 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
                 *reinterpret_cast<uint4*>(out + (long long)grow * p.ldo + n0 + ch * 8) = val;
               }
             }
-            __syncwarp();
           } else {
             // 32 fp32 = 128 B per row, 16 B chunks XOR-swizzled with row&7 (conflict-free both ways)
 #pragma unroll
@@ -668,7 +685,6 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
                 *reinterpret_cast<float4*>(out + (long long)grow * p.ldo + n0 + ch * 4) = val;
               }
             }
-            __syncwarp();
           }
         }
       }
