@@ -15,133 +15,179 @@
 namespace pn {
 
 constexpr int GN_GROUPS = 32;
-constexpr int GN_CHUNK = 64;  // pixels per partial-statistics block
+constexpr int GN_THREADS = 512;
+constexpr int GN_MAX_FRAMES = 1024;
+constexpr size_t GN_WAVE_BYTES = 56ull << 20;   // frames processed together: their fp32 input stays resident in L2
 
-// ---------------------------------------------------------------- spatial GN: partial sums per pixel chunk
-// partial[f][chunk][g][2] = (sum, sumsq) over the chunk's pixels x group channels (fp32, <= 64*cpg terms each).
-// Thread layout: (pixel lane, float4 column). With C = 320 a block of 256 threads runs 3 pixel lanes x 80 columns,
-// so (almost) every thread streams; per-lane column sums meet in shared memory and are reduced in a fixed order
-// (bit-reproducible, no atomics).
-__global__ void __launch_bounds__(256) gn_partial_kernel(const float* __restrict__ x, float* __restrict__ partial,
-                                                         int P, int C, int nchunks, int PL) {
-  extern __shared__ float colacc[];   // [PL][2][C]
-  const int f = blockIdx.y, chunk = blockIdx.x;
-  const int cpg = C / GN_GROUPS;
-  const int p0 = chunk * GN_CHUNK;
-  const int p1 = min(P, p0 + GN_CHUNK);
-  const int c4n = C / 4;
-  const float* base = x + ((size_t)f * P) * C;
-  const int cols = c4n < 256 ? c4n : 256;
-  const int pl = threadIdx.x / cols;
-  if (pl < PL) {
-    for (int c4 = threadIdx.x - pl * cols; c4 < c4n; c4 += cols) {
-      float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int p = p0 + pl; p < p1; p += PL) {
-        const float4 v = *reinterpret_cast<const float4*>(base + (size_t)p * C + c4 * 4);
-        s[0] += v.x; q[0] += v.x * v.x;
-        s[1] += v.y; q[1] += v.y * v.y;
-        s[2] += v.z; q[2] += v.z * v.z;
-        s[3] += v.w; q[3] += v.w * v.w;
-      }
-      *reinterpret_cast<float4*>(colacc + (size_t)pl * 2 * C + c4 * 4) = make_float4(s[0], s[1], s[2], s[3]);
-      *reinterpret_cast<float4*>(colacc + (size_t)pl * 2 * C + C + c4 * 4) = make_float4(q[0], q[1], q[2], q[3]);
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x < GN_GROUPS * 2) {
-    const int g = threadIdx.x >> 1, which = threadIdx.x & 1;
-    float acc = 0.f;
-    for (int l = 0; l < PL; ++l) {
-      const float* src = colacc + (size_t)l * 2 * C + which * C + g * cpg;
-      for (int j = 0; j < cpg; ++j) acc += src[j];
-    }
-    partial[((size_t)f * nchunks + chunk) * GN_GROUPS * 2 + threadIdx.x] = acc;
-  }
-}
+// arrival / departure counters of the per-frame CTA groups; zero at module load and reset by the last CTA to leave
+__device__ unsigned int g_gn_arrive[GN_MAX_FRAMES];
+__device__ unsigned int g_gn_depart[GN_MAX_FRAMES];
 
-// scale[f][c] = rstd*gamma[c]; shift[f][c] = beta[c] - mean*rstd*gamma[c]   (double-precision combine)
-__global__ void gn_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* __restrict__ scale,
-                                   float* __restrict__ shift, int P, int C, int nchunks, float eps) {
-  __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
-  __shared__ double s_part[4][GN_GROUPS * 2];
-  const int f = blockIdx.x;
-  const int cpg = C / GN_GROUPS;
-  {
-    // 256 threads: (chunk quarter, group, sum|sumsq); double-precision combine in a fixed order
-    const int slot = threadIdx.x & 63, quarter = threadIdx.x >> 6;
-    double acc = 0.0;
-    const float* pp = partial + (size_t)f * nchunks * GN_GROUPS * 2 + slot;
-    for (int k = quarter; k < nchunks; k += 4) acc += (double)pp[(size_t)k * GN_GROUPS * 2];
-    s_part[quarter][slot] = acc;
-  }
-  __syncthreads();
-  if (threadIdx.x < GN_GROUPS) {
-    const int g = threadIdx.x;
-    const double s = (s_part[0][2 * g] + s_part[1][2 * g]) + (s_part[2][2 * g] + s_part[3][2 * g]);
-    const double q = (s_part[0][2 * g + 1] + s_part[1][2 * g + 1]) + (s_part[2][2 * g + 1] + s_part[3][2 * g + 1]);
-    const double n = (double)P * cpg;
-    const double mean = s / n;
-    double var = q / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    s_mean[threadIdx.x] = (float)mean;
-    s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
-    const float sc = s_rstd[g] * gamma[c];
-    scale[(size_t)f * C + c] = sc;
-    shift[(size_t)f * C + c] = beta[c] - s_mean[g] * sc;
-  }
-}
-
-// y = act(x*scale[f,c] + shift[f,c]) -> bf16 ; optional raw bf16 copy of x (input of the 1x1 skip conv).
-// Thread layout: (pixel lane, 8-channel column) fixed per thread, so scale/shift live in registers and the loop has
-// no integer division; a block covers GN_APPLY_PIX pixels of one frame.
-constexpr int GN_APPLY_PIX = 64;
-__global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ scale,
-                                                       const float* __restrict__ shift,
-                                                       __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ raw,
-                                                       int P, int C, int act_silu) {
-  const int f = blockIdx.y;
+// ---------------------------------------------------------------- spatial GN (+SiLU) -> bf16, ONE launch
+// The statistics of a frame need every pixel of it before the first output can be written, so the input is read
+// twice; done as two kernels over the whole tensor the second read comes from HBM again (220 MB at level 0). Here the
+// frames are processed in waves small enough to stay in L2: `cpf` co-resident CTAs share one frame, each
+//   1. accumulates (sum, sumsq) per group over its pixel range (fixed order: bit-reproducible, no float atomics),
+//   2. publishes them and waits for the other CTAs of the frame (one integer atomic per CTA),
+//   3. combines all partials of the frame in double precision (every CTA does the same sum in the same order),
+//   4. normalises ITS OWN pixel range again (L2 hits) -> y = act(x * rstd * gamma + beta - mean * rstd * gamma).
+// Thread layout in both passes: (pixel lane, 8-channel column), so scale/shift live in registers in pass 4.
+// partial: [frames][cpf][32 groups][2] floats.
+__global__ void __launch_bounds__(GN_THREADS, 1)
+gn_fused_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ raw, float* __restrict__ partial, int P, int C,
+                int F, int wave, int cpf, float eps, int act_silu) {
+  extern __shared__ float gn_smem[];
   const int c8n = C / 8;
-  const int cols = c8n < 256 ? c8n : 256;
-  const int PL = 256 / cols;
+  const int cols = c8n < GN_THREADS ? c8n : GN_THREADS;
+  const int PL = GN_THREADS / cols;                 // pixel lanes
+  float* colacc = gn_smem;                          // [PL][2][C]
+  float* s_scale = gn_smem + (size_t)PL * 2 * C;    // [C]
+  float* s_shift = s_scale + C;                     // [C]
+  __shared__ double s_part[8][GN_GROUPS * 2];
+  __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
+  const int cpg = C / GN_GROUPS;
   const int pl = threadIdx.x / cols;
-  if (pl >= PL) return;
-  const int p0 = blockIdx.x * GN_APPLY_PIX;
-  const int p1 = min(P, p0 + GN_APPLY_PIX);
-  const float* xb = x + (size_t)f * P * C;
-  __nv_bfloat16* yb = y + (size_t)f * P * C;
-  __nv_bfloat16* rb = raw ? raw + (size_t)f * P * C : nullptr;
-  for (int c8 = threadIdx.x - pl * cols; c8 < c8n; c8 += cols) {
-    float sc[8], sh[8];
-    {
-      const float4 a = *reinterpret_cast<const float4*>(scale + (size_t)f * C + c8 * 8);
-      const float4 b = *reinterpret_cast<const float4*>(scale + (size_t)f * C + c8 * 8 + 4);
-      const float4 c = *reinterpret_cast<const float4*>(shift + (size_t)f * C + c8 * 8);
-      const float4 d = *reinterpret_cast<const float4*>(shift + (size_t)f * C + c8 * 8 + 4);
-      sc[0] = a.x; sc[1] = a.y; sc[2] = a.z; sc[3] = a.w; sc[4] = b.x; sc[5] = b.y; sc[6] = b.z; sc[7] = b.w;
-      sh[0] = c.x; sh[1] = c.y; sh[2] = c.z; sh[3] = c.w; sh[4] = d.x; sh[5] = d.y; sh[6] = d.z; sh[7] = d.w;
-    }
-    for (int p = p0 + pl; p < p1; p += PL) {
-      const size_t off = (size_t)p * C + (size_t)c8 * 8;
-      const float4 a = *reinterpret_cast<const float4*>(xb + off);
-      const float4 b = *reinterpret_cast<const float4*>(xb + off + 4);
-      float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-      if (rb) {
-        *reinterpret_cast<uint4*>(rb + off) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
-                                                          pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-      }
+  const int col0 = threadIdx.x - pl * cols;
+  const int fi = blockIdx.x / cpf, r = blockIdx.x - fi * cpf;
+  if (fi >= wave) return;
+  const int ppc = (P + cpf - 1) / cpf;              // pixels per CTA
+  const int p0 = r * ppc, p1 = min(P, p0 + ppc);
+
+  for (int f = fi; f < F; f += wave) {
+    const float* xb = x + (size_t)f * P * C;
+    // ---- pass 1: per-thread column sums over this CTA's pixels
+    if (pl < PL) {
+      for (int c8 = col0; c8 < c8n; c8 += cols) {
+        float s[8], q[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float t = v[j] * sc[j] + sh[j];
-        v[j] = act_silu ? silu(t) : t;
+        for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+        int p = p0 + pl;
+        for (; p + 3 * PL < p1; p += 4 * PL) {      // four pixels in flight per thread
+          float4 a[4], b[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float* src = xb + (size_t)(p + u * PL) * C + (size_t)c8 * 8;
+            a[u] = *reinterpret_cast<const float4*>(src);
+            b[u] = *reinterpret_cast<const float4*>(src + 4);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            s[0] += a[u].x; q[0] += a[u].x * a[u].x; s[1] += a[u].y; q[1] += a[u].y * a[u].y;
+            s[2] += a[u].z; q[2] += a[u].z * a[u].z; s[3] += a[u].w; q[3] += a[u].w * a[u].w;
+            s[4] += b[u].x; q[4] += b[u].x * b[u].x; s[5] += b[u].y; q[5] += b[u].y * b[u].y;
+            s[6] += b[u].z; q[6] += b[u].z * b[u].z; s[7] += b[u].w; q[7] += b[u].w * b[u].w;
+          }
+        }
+        for (; p < p1; p += PL) {
+          const float* src = xb + (size_t)p * C + (size_t)c8 * 8;
+          const float4 a = *reinterpret_cast<const float4*>(src);
+          const float4 b = *reinterpret_cast<const float4*>(src + 4);
+          s[0] += a.x; q[0] += a.x * a.x; s[1] += a.y; q[1] += a.y * a.y; s[2] += a.z; q[2] += a.z * a.z;
+          s[3] += a.w; q[3] += a.w * a.w; s[4] += b.x; q[4] += b.x * b.x; s[5] += b.y; q[5] += b.y * b.y;
+          s[6] += b.z; q[6] += b.z * b.z; s[7] += b.w; q[7] += b.w * b.w;
+        }
+        float* dst = colacc + (size_t)pl * 2 * C + (size_t)c8 * 8;
+        *reinterpret_cast<float4*>(dst) = make_float4(s[0], s[1], s[2], s[3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(s[4], s[5], s[6], s[7]);
+        *reinterpret_cast<float4*>(dst + C) = make_float4(q[0], q[1], q[2], q[3]);
+        *reinterpret_cast<float4*>(dst + C + 4) = make_float4(q[4], q[5], q[6], q[7]);
       }
-      *reinterpret_cast<uint4*>(yb + off) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
-                                                        pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
     }
+    __syncthreads();
+    float* my_partial = partial + ((size_t)f * cpf + r) * GN_GROUPS * 2;
+    if (threadIdx.x < GN_GROUPS * 2) {
+      const int g = threadIdx.x >> 1, which = threadIdx.x & 1;
+      float acc = 0.f;
+      for (int l = 0; l < PL; ++l) {
+        const float* src = colacc + (size_t)l * 2 * C + which * C + g * cpg;
+        for (int j = 0; j < cpg; ++j) acc += src[j];
+      }
+      my_partial[threadIdx.x] = acc;
+      __threadfence();
+    }
+    __syncthreads();
+    // ---- frame barrier among the cpf CTAs of this frame
+    if (threadIdx.x == 0) {
+      atomicAdd(&g_gn_arrive[f], 1u);
+      while (*reinterpret_cast<volatile unsigned int*>(&g_gn_arrive[f]) < (unsigned int)cpf) __nanosleep(64);
+      __threadfence();
+    }
+    __syncthreads();
+    // ---- combine all partials of the frame (double precision, fixed order, identical in every CTA)
+    {
+      const int slot = threadIdx.x & 63, part = threadIdx.x >> 6;      // 8 interleaved partial sums per slot
+      double acc = 0.0;
+      const float* pp = partial + (size_t)f * cpf * GN_GROUPS * 2 + slot;
+      for (int k = part; k < cpf; k += GN_THREADS / 64) acc += (double)__ldcg(pp + (size_t)k * GN_GROUPS * 2);
+      s_part[part][slot] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {     // every read of the counters and partials of this frame by this CTA is done
+      const unsigned int old = atomicAdd(&g_gn_depart[f], 1u);
+      if (old == (unsigned int)cpf - 1u) { g_gn_arrive[f] = 0u; g_gn_depart[f] = 0u; }
+    }
+    if (threadIdx.x < GN_GROUPS) {
+      const int g = threadIdx.x;
+      double sm = 0.0, sq = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { sm += s_part[k][2 * g]; sq += s_part[k][2 * g + 1]; }
+      const double n = (double)P * cpg;
+      const double mean = sm / n;
+      double var = sq / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      s_mean[g] = (float)mean;
+      s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += GN_THREADS) {
+      const int g = c / cpg;
+      const float sc = s_rstd[g] * gamma[c];
+      s_scale[c] = sc;
+      s_shift[c] = beta[c] - s_mean[g] * sc;
+    }
+    __syncthreads();
+    // ---- pass 2: normalise this CTA's pixel range (second read of x: L2)
+    __nv_bfloat16* yb = y + (size_t)f * P * C;
+    __nv_bfloat16* rb = raw ? raw + (size_t)f * P * C : nullptr;
+    if (pl < PL) {
+      for (int c8 = col0; c8 < c8n; c8 += cols) {
+        float sc[8], sh[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sc[j] = s_scale[c8 * 8 + j]; sh[j] = s_shift[c8 * 8 + j]; }
+        auto emit = [&](size_t off, const float4& a, const float4& b) {
+          float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+          if (rb) {
+            *reinterpret_cast<uint4*>(rb + off) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                              pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float t = v[j] * sc[j] + sh[j];
+            v[j] = act_silu ? silu(t) : t;
+          }
+          *reinterpret_cast<uint4*>(yb + off) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                            pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        };
+        int p = p0 + pl;
+        for (; p + 3 * PL < p1; p += 4 * PL) {      // four pixels in flight per thread
+          float4 a[4], b[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float* src = xb + (size_t)(p + u * PL) * C + (size_t)c8 * 8;
+            a[u] = *reinterpret_cast<const float4*>(src);
+            b[u] = *reinterpret_cast<const float4*>(src + 4);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) emit((size_t)(p + u * PL) * C + (size_t)c8 * 8, a[u], b[u]);
+        }
+        for (; p < p1; p += PL) {
+          const size_t off = (size_t)p * C + (size_t)c8 * 8;
+          emit(off, *reinterpret_cast<const float4*>(xb + off), *reinterpret_cast<const float4*>(xb + off + 4));
+        }
+      }
+    }
+    __syncthreads();      // colacc / s_scale are rewritten by the next frame of this CTA
   }
 }
 
@@ -256,9 +302,27 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 
 using namespace pn;
 
+// wave = frames processed concurrently (their input fits L2), cpf = CTAs per frame; wave * cpf <= SM count
+static void gn_geometry(int64_t frames, int64_t pixels, int64_t channels, int* wave, int* cpf) {
+  const size_t frame_bytes = (size_t)pixels * channels * sizeof(float);
+  int w = (int)(GN_WAVE_BYTES / (frame_bytes ? frame_bytes : 1));
+  if (w < 1) w = 1;
+  if (w > frames) w = (int)frames;
+  const int sms = sm_count();
+  if (w > sms) w = sms;
+  for (int d = w; 2 * d > w; --d)                 // prefer a wave that divides the frame count (no idle last wave)
+    if (frames % d == 0) { w = d; break; }
+  int c = sms / w;
+  const int max_c = (int)((pixels + 7) / 8);      // at least 8 pixels per CTA
+  if (c > max_c) c = max_c < 1 ? 1 : max_c;
+  *wave = w;
+  *cpf = c;
+}
+
 extern "C" int64_t pn_groupnorm_workspace_floats(int64_t frames, int64_t pixels, int64_t channels) {
-  const int64_t nchunks = (pixels + GN_CHUNK - 1) / GN_CHUNK;
-  return frames * nchunks * GN_GROUPS * 2 + 2 * frames * channels;
+  int wave, cpf;
+  gn_geometry(frames, pixels, channels, &wave, &cpf);
+  return frames * cpf * GN_GROUPS * 2;
 }
 
 extern "C" int pn_groupnorm_silu(const float* x, const float* gamma, const float* beta, void* y_bf16,
@@ -268,21 +332,25 @@ extern "C" int pn_groupnorm_silu(const float* x, const float* gamma, const float
   PN_REQUIRE(channels % 32 == 0 && channels % 8 == 0 && channels <= 8192, "pn_groupnorm_silu: C=%lld unsupported",
              (long long)channels);
   PN_REQUIRE(frames > 0 && pixels > 0, "pn_groupnorm_silu: empty input");
+  PN_REQUIRE(frames <= GN_MAX_FRAMES, "pn_groupnorm_silu: more than %d frames", GN_MAX_FRAMES);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
   const int P = (int)pixels, C = (int)channels, F = (int)frames;
-  const int nchunks = (P + GN_CHUNK - 1) / GN_CHUNK;
-  float* partial = workspace;
-  float* scale = workspace + (size_t)F * nchunks * GN_GROUPS * 2;
-  float* shift = scale + (size_t)F * C;
-  const int c4n = C / 4;
-  const int PL = c4n < 256 ? 256 / c4n : 1;
-  gn_partial_kernel<<<dim3(nchunks, F), 256, (size_t)PL * 2 * C * sizeof(float), st>>>(x, partial, P, C, nchunks, PL);
-  PN_CHECK_CUDA(cudaGetLastError());
-  gn_finalize_kernel<<<F, 256, 0, st>>>(partial, gamma, beta, scale, shift, P, C, nchunks, eps);
-  PN_CHECK_CUDA(cudaGetLastError());
-  const int gx = (P + GN_APPLY_PIX - 1) / GN_APPLY_PIX;
-  gn_apply_kernel<<<dim3(gx, F), 256, 0, st>>>(x, scale, shift, reinterpret_cast<__nv_bfloat16*>(y_bf16),
-                                                reinterpret_cast<__nv_bfloat16*>(raw_bf16), P, C, act_silu);
+  int wave, cpf;
+  gn_geometry(frames, pixels, channels, &wave, &cpf);
+  const int c8n = C / 8;
+  const int cols = c8n < GN_THREADS ? c8n : GN_THREADS;
+  const int PL = GN_THREADS / cols;
+  const size_t smem = ((size_t)PL * 2 * C + 2 * (size_t)C) * sizeof(float);
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    PN_CHECK_CUDA(cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  // all wave * cpf CTAs spin on each other: they are co-resident because the grid never exceeds the SM count and the
+  // kernel is limited to one CTA per SM
+  gn_fused_kernel<<<wave * cpf, GN_THREADS, smem, st>>>(x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y_bf16),
+                                                        reinterpret_cast<__nv_bfloat16*>(raw_bf16), workspace, P, C, F,
+                                                        wave, cpf, eps, act_silu);
   PN_CHECK_CUDA(cudaGetLastError());
   return PN_OK;
 }

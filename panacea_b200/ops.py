@@ -134,7 +134,7 @@ class NativeOps:
         ws = torch.empty(nws, device=x.device, dtype=F32)
         _lib.check(self.lib.pn_groupnorm_silu(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(raw), _ptr(ws), Fr, P, Cc,
                                              float(eps), int(bool(silu)), _stream()), "pn_groupnorm_silu")
-        self.launches += 3
+        self.launches += 1
         return (y, raw) if want_raw else y
 
     def groupnorm_pixel(self, x, gamma, beta, eps, silu):
