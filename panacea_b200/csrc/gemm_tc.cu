@@ -56,6 +56,7 @@ struct GemmParams {
   int rows_per_group, n_groups;
   int out_bf16;
   int geglu;
+  int bstat;                   // weight-stationary schedule (K = 5 k-blocks, taps = 1): see gemm_tc_kernel
 };
 
 template <int BN, int STAGES, int NCTA, int MODE>
@@ -72,7 +73,8 @@ struct GemmSmem {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int RING_BYTES = MODE == 6 ? HALO_STAGES * A_HALO_BYTES + STAGES * B_BYTES : STAGES * STAGE_BYTES;
   static constexpr int STAGING_BYTES = gemm_streaming(MODE) ? (BN / 32) * RCHUNK_BYTES : NEPI * STAGE_WARP_BYTES;
-  static constexpr int ROWMAP_BYTES = gemm_streaming(MODE) ? 0 : NEPI * 32 * 4;
+  static constexpr bool BIAS_SMEM = (MODE == 1 || MODE == 2);    // the ALU-bound epilogues stage their bias slice in smem
+  static constexpr int ROWMAP_BYTES = gemm_streaming(MODE) ? 0 : NEPI * 32 * 4 + (BIAS_SMEM ? NEPI * 512 : 0);
   static constexpr int BAR_BYTES = (2 * STAGES + 4 + 2 * (BN / 32) + 8) * 8 + 16;
   static constexpr int TOTAL = RING_BYTES + STAGING_BYTES + ROWMAP_BYTES + BAR_BYTES + 1024;
 };
@@ -105,6 +107,8 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
   uint64_t* c_ready = r_full + BN / 32;       // [BN/32]  MODE 4: chunk updated by its 4 epilogue warps -> store it
   uint64_t* a_full = c_ready + BN / 32;       // [3]      MODE 6: haloed A tiles
   uint64_t* a_empty = a_full + 4;             // [3]
+  uint64_t* b_full = a_full;                  // [5]      weight-stationary: resident weight k-blocks (modes other than 6)
+  uint64_t* b_empty = a_empty + 1;            // [1]      ... all MMAs reading them have retired
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(a_empty + 4);
 
   const int warp = threadIdx.x >> 5;
@@ -120,6 +124,27 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
   const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
   const int tiles_m_units = (tiles_m + NCTA - 1) / NCTA;
   const int num_tiles = tiles_m_units * p.tiles_col;
+  // Tile schedule. Default: tile = unit + i * num_units, column tile fastest (concurrent units share an A tile in L2).
+  // Weight-stationary (p.bstat, the K = 320 linears of level 0 whose k loop is only 5 blocks long and L2->SM bound):
+  // unit u keeps ONE column tile (u mod tiles_col) for the whole launch — its weight tile (all 5 k-blocks, parked in
+  // the B halves of ring stages 0..4) is loaded once — and walks a contiguous range of row tiles; the tiles_col units
+  // of a row range advance together, so they still share each A tile in L2. Per k-block only the 16 KB A tile crosses
+  // the L2->SM fabric instead of A + B. (num_units mod tiles_col units stay idle.)
+  int t_begin, t_step, t_count;
+  if (p.bstat) {
+    const int ranges = num_units / p.tiles_col;
+    const int col = unit % p.tiles_col, r = unit / p.tiles_col;
+    const int per = tiles_m_units / ranges, rem = tiles_m_units % ranges;
+    t_begin = col * tiles_m_units + r * per + (r < rem ? r : rem);      // column-major tile index
+    t_count = r < ranges ? per + (r < rem ? 1 : 0) : 0;
+    t_step = 1;
+  } else {
+    t_begin = unit;
+    t_step = num_units;
+    t_count = unit < num_tiles ? (num_tiles - unit + num_units - 1) / num_units : 0;
+  }
+  auto tile_col = [&](int tile) { return p.bstat ? tile / tiles_m_units : tile % p.tiles_col; };
+  auto tile_mu = [&](int tile) { return p.bstat ? tile % tiles_m_units : tile / p.tiles_col; };
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static_assert(2 * BN <= 512, "two accumulator stages must fit TMEM");
 
@@ -139,6 +164,9 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
         mbar_init(&a_full[i], 1);
         mbar_init(&a_empty[i], 1);
       }
+    } else {
+      for (int i = 0; i < 5; ++i) mbar_init(&b_full[i], 1);
+      mbar_init(b_empty, 1);
     }
     if (gemm_streaming(MODE)) {
       tma_prefetch_desc(&p.mapOut);
@@ -171,9 +199,9 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
     uint8_t* ringB = stage_base + S::HALO_STAGES * S::A_HALO_BYTES;
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
-    for (int tile = unit; tile < num_tiles; tile += num_units) {
-      const int tcol = tile % p.tiles_col;
-      int tm = (tile / p.tiles_col) * NCTA + (int)cta_rank;
+    for (int ti = 0, tile = t_begin; ti < t_count; ++ti, tile += t_step) {
+      const int tcol = tile_col(tile);
+      int tm = tile_mu(tile) * NCTA + (int)cta_rank;
       const int twi = tm % p.tiles_w; tm /= p.tiles_w;
       const int thi = tm % p.tiles_h; tm /= p.tiles_h;
       const int x0 = twi * p.tw, y0 = thi * p.th, n0 = tm * p.tn;
@@ -219,7 +247,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
       const uint64_t descB0 = umma_smem_desc(ringB, 16, 1024);
       int sa = 0, sb = 0, acc = 0;
       uint32_t pa = 0, pb = 0, acc_phase = 0;
-      for (int tile = unit; tile < num_tiles; tile += num_units) {
+      for (int ti = 0, tile = t_begin; ti < t_count; ++ti, tile += t_step) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -262,14 +290,34 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
     int stage = 0;
     uint32_t phase = 0;
     bool first = true;
-    for (int tile = unit; tile < num_tiles; tile += num_units) {
-      const int tcol = tile % p.tiles_col;
-      int tm = (tile / p.tiles_col) * NCTA + (int)cta_rank;
+    int cur_col = -1;
+    uint32_t bgen = 0;                            // weight-stationary: weight tiles loaded so far
+    for (int ti = 0, tile = t_begin; ti < t_count; ++ti, tile += t_step) {
+      const int tcol = tile_col(tile);
+      int tm = tile_mu(tile) * NCTA + (int)cta_rank;
       const int twi = tm % p.tiles_w; tm /= p.tiles_w;
       const int thi = tm % p.tiles_h; tm /= p.tiles_h;
       const int tni = tm;                       // >= tiles_n for the odd tail of a pair: fully OOB -> zero fill
       const int x0 = twi * p.tw, y0 = thi * p.th, n0 = tni * p.tn;
       const int bn0 = tcol * BN + (NCTA == 2 ? (int)cta_rank * (BN / 2) : 0);
+      if (MODE != 6 && p.bstat && tcol != cur_col) {
+        // new column tile: once every MMA that reads the resident weight tile has retired, replace all its k-blocks
+        if (bgen > 0) mbar_wait(b_empty, (bgen - 1) & 1);
+        if (elect_one()) {
+          for (int kb = 0; kb < num_k_blocks; ++kb) {
+            uint8_t* sB = stage_base + kb * S::STAGE_BYTES + S::A_BYTES;
+            if (NCTA == 2) {
+              if (cta_rank == 0) mbar_arrive_expect_tx(&b_full[kb], 2 * S::B_BYTES);
+              tma_load_2d_2sm(sB, &p.mapB, &b_full[kb], kb * BK, bn0);
+            } else {
+              mbar_arrive_expect_tx(&b_full[kb], S::B_BYTES);
+              tma_load_2d(sB, &p.mapB, &b_full[kb], kb * BK, bn0);
+            }
+          }
+        }
+        cur_col = tcol;
+        ++bgen;
+      }
       int kc = 0, dx = -p.pad_w, dy = -p.pad_h;   // k-block -> (tap row, tap column, channel chunk), kept incrementally
       for (int kb = 0; kb < num_k_blocks; ++kb) {
         if (!(p.debug == 1 && !(first && kb < STAGES))) {   // experiment 1: the ring is filled once, never again
@@ -277,14 +325,15 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
           if (elect_one()) {
             uint8_t* sA = stage_base + stage * S::STAGE_BYTES;
             uint8_t* sB = sA + S::A_BYTES;
+            const uint32_t tx = (MODE != 6 && p.bstat) ? S::A_BYTES : S::STAGE_BYTES;
             if (NCTA == 2) {
-              if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);   // bytes of both CTAs
+              if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * tx);   // bytes of both CTAs
               tma_load_4d_2sm(sA, &p.mapA, &full_bar[stage], kc * BK, x0 + dx, y0 + dy, n0);
-              tma_load_2d_2sm(sB, &p.mapB, &full_bar[stage], kb * BK, bn0);
+              if (!(MODE != 6 && p.bstat)) tma_load_2d_2sm(sB, &p.mapB, &full_bar[stage], kb * BK, bn0);
             } else {
-              mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+              mbar_arrive_expect_tx(&full_bar[stage], tx);
               tma_load_4d(sA, &p.mapA, &full_bar[stage], kc * BK, x0 + dx, y0 + dy, n0);
-              tma_load_2d(sB, &p.mapB, &full_bar[stage], kb * BK, bn0);
+              if (!(MODE != 6 && p.bstat)) tma_load_2d(sB, &p.mapB, &full_bar[stage], kb * BK, bn0);
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -311,16 +360,24 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
       int acc = 0;
       uint32_t acc_phase = 0;
       bool first = true;
-      for (int tile = unit; tile < num_tiles; tile += num_units) {
+      int cur_col = -1;
+      uint32_t bgen = 0;
+      for (int ti = 0, tile = t_begin; ti < t_count; ++ti, tile += t_step) {
+        const bool bstat = MODE != 6 && p.bstat;
+        const int tcol = tile_col(tile);
+        const bool new_b = bstat && tcol != cur_col;              // first tile on a freshly loaded weight tile
+        if (new_b) { cur_col = tcol; ++bgen; }
+        const bool last_b = bstat && (ti + 1 == t_count || tile_col(tile + t_step) != tcol);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           if (!(p.debug == 1 && !(first && kb < STAGES))) mbar_wait(&full_bar[stage], phase);
+          if (new_b) mbar_wait(&b_full[kb], (bgen - 1) & 1);
           tc_fence_after();
           if (elect_one()) {
             const uint64_t da = descA0 + STAGE_STEP * stage;
-            const uint64_t db = descB0 + STAGE_STEP * stage;
+            const uint64_t db = descB0 + STAGE_STEP * (bstat ? kb : stage);
             if (p.debug != 2) {
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) {
@@ -329,12 +386,15 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
               }
             }
             // commit: frees the smem slot (in both CTAs) once the MMAs retire; the last one also publishes the tile
+            const bool last_kb = kb == num_k_blocks - 1;
             if (NCTA == 2) {
               umma_commit_2sm(&empty_bar[stage], 3);
-              if (kb == num_k_blocks - 1) umma_commit_2sm(&tmem_full[acc], 3);
+              if (last_kb) umma_commit_2sm(&tmem_full[acc], 3);
+              if (last_kb && last_b) umma_commit_2sm(b_empty, 3);
             } else {
               umma_commit(&empty_bar[stage]);
-              if (kb == num_k_blocks - 1) umma_commit(&tmem_full[acc]);
+              if (last_kb) umma_commit(&tmem_full[acc]);
+              if (last_kb && last_b) umma_commit(b_empty);
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -349,9 +409,9 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
       constexpr int NCH = BN / 32;
       bool first = true;
       int it = 0;
-      for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
-        const int tcol = tile % p.tiles_col;
-        int tm = (tile / p.tiles_col) * NCTA + (int)cta_rank;
+      for (int ti = 0, tile = t_begin; ti < t_count; ++ti, tile += t_step, ++it) {
+        const int tcol = tile_col(tile);
+        int tm = tile_mu(tile) * NCTA + (int)cta_rank;
         const int twi = tm % p.tiles_w; tm /= p.tiles_w;
         const int thi = tm % p.tiles_h; tm /= p.tiles_h;
         const int m0 = (tm * p.H + thi) * p.W + twi * p.tw;      // th == tn == 1: 128 consecutive output rows
@@ -367,14 +427,15 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
           }
           first = false;
         }
-        const int ntile = tile + num_units;
+        const int ntile = tile + t_step;
+        const bool has_next = ti + 1 < t_count;
         int nm0 = 0, nn0 = 0;
-        if (ntile < num_tiles) {
-          int t2 = (ntile / p.tiles_col) * NCTA + (int)cta_rank;
+        if (has_next) {
+          int t2 = tile_mu(ntile) * NCTA + (int)cta_rank;
           const int w2 = t2 % p.tiles_w; t2 /= p.tiles_w;
           const int h2 = t2 % p.tiles_h; t2 /= p.tiles_h;
           nm0 = (t2 * p.H + h2) * p.W + w2 * p.tw;
-          nn0 = (ntile % p.tiles_col) * BN;
+          nn0 = tile_col(ntile) * BN;
         }
         // all chunk stores are issued back to back (one bulk group each); a chunk's buffer is only handed on once
         // ITS group has been read out of shared memory — waiting per store serialised the store warp
@@ -387,7 +448,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           tma_store_wait_read_le(NCH - 1 - c);         // groups complete in order: chunk c has left shared memory
-          if (ntile < num_tiles) {
+          if (has_next) {
             if (p.has_res) {
               mbar_arrive_expect_tx(&r_full[c], S::RCHUNK_BYTES);
               tma_load_2d(staging + c * S::RCHUNK_BYTES, &p.mapRes, &r_full[c], nn0 + c * 32, nm0);
@@ -410,9 +471,9 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
     const uint32_t te_addr0 = (NCTA == 2) ? mapa_shared(smem_u32(&tmem_empty[0]), 0) : smem_u32(&tmem_empty[0]);
     int acc = 0, it = 0;
     uint32_t acc_phase = 0;
-    for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
-      const int tcol = tile % p.tiles_col;
-      int tm = (tile / p.tiles_col) * NCTA + (int)cta_rank;
+    for (int ti = 0, tile = t_begin; ti < t_count; ++ti, tile += t_step, ++it) {
+      const int tcol = tile_col(tile);
+      int tm = tile_mu(tile) * NCTA + (int)cta_rank;
       const int twi = tm % p.tiles_w; tm /= p.tiles_w;
       const int thi = tm % p.tiles_h; tm /= p.tiles_h;
       const long long grow = (long long)(tm * p.H + thi) * p.W + twi * p.tw + r;
@@ -495,6 +556,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
     const int half = ew >> 2;                    // chunk residue class of this warp
     uint8_t* my_stage = staging + ew * S::STAGE_WARP_BYTES;
     int* my_rowmap = rowmap + ew * 32;
+    float* my_bias = reinterpret_cast<float*>(rowmap + NEPI * 32) + ew * 128;   // bias of this warp's <= 4 chunks
     constexpr int NCH = BN / 32;
     constexpr int MYCH = (NCH + EG - 1) / EG;
     constexpr int PRECH = MYCH < 2 ? MYCH : 2;   // chunks whose residual is prefetched at tile start (register budget:
@@ -507,9 +569,9 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
       if (NCTA == 2) mbar_arrive_cluster(te_addr0 + a * 8);
       else mbar_arrive(&tmem_empty[a]);
     };
-    for (int tile = unit; tile < num_tiles; tile += num_units) {
-      const int tcol = tile % p.tiles_col;
-      int tm = (tile / p.tiles_col) * NCTA + (int)cta_rank;
+    for (int ti = 0, tile = t_begin; ti < t_count; ++ti, tile += t_step) {
+      const int tcol = tile_col(tile);
+      int tm = tile_mu(tile) * NCTA + (int)cta_rank;
       const int twi = tm % p.tiles_w; tm /= p.tiles_w;
       const int thi = tm % p.tiles_h; tm /= p.tiles_h;
       const int tni = tm;
@@ -523,9 +585,18 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
         const bool ok = (x < p.W) && (y < p.H) && (n < p.NB);
         my_rowmap[lane] = ok ? ((n * p.H + y) * p.W + x) : -1;
       }
+      const int n_base = tcol * BN;
+      // bias slice of this warp's chunks -> shared memory now, while the accumulator is still being computed (a global
+      // load per chunk inside the epilogue left the warps on the long scoreboard for a third of their time)
+      if (S::BIAS_SMEM && p.bias != nullptr) {
+#pragma unroll
+        for (int k = 0; k < MYCH; ++k) {
+          const int n = n_base + (half + EG * k) * 32 + lane;
+          my_bias[k * 32 + lane] = (half + EG * k < NCH && n < p.N) ? __ldg(p.bias + n) : 0.f;
+        }
+      }
       __syncwarp();
       const int my_row = my_rowmap[lane];
-      const int n_base = tcol * BN;
       // ---- residual prefetch (fp32 output path): lane -> (row i*4 + lane/8, 16-byte column chunk lane%8)
       float4 rpre[PRECH][8];
       const bool pre = (MODE == 0 || MODE == 3) && (p.residual != nullptr);
@@ -571,11 +642,11 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
           if (p.bias != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              if (n0 + j < p.N) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-                f2_unpack(f2_add(f2_pack(f[j], f[j + 1]), f2_pack(b4.x, b4.y)), f[j], f[j + 1]);
-                f2_unpack(f2_add(f2_pack(f[j + 2], f[j + 3]), f2_pack(b4.z, b4.w)), f[j + 2], f[j + 3]);
-              }
+              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (S::BIAS_SMEM) b4 = *reinterpret_cast<const float4*>(my_bias + k * 32 + j);   // broadcast read; 0 beyond N
+              else if (n0 + j < p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+              f2_unpack(f2_add(f2_pack(f[j], f[j + 1]), f2_pack(b4.x, b4.y)), f[j], f[j + 1]);
+              f2_unpack(f2_add(f2_pack(f[j + 2], f[j + 3]), f2_pack(b4.z, b4.w)), f[j + 2], f[j + 3]);
             }
           }
           if (p.rowvec != nullptr && my_row >= 0) {
@@ -712,6 +783,15 @@ static int gemm_stream_kmax() {
     kmax = e ? atoi(e) : 1920;
   }
   return kmax;
+}
+
+static int gemm_bstat_enabled() {   // PN_GEMM_BSTAT=0 disables the weight-stationary schedule (A/B measurements)
+  static int m = -1;
+  if (m < 0) {
+    const char* e = getenv("PN_GEMM_BSTAT");
+    m = e ? atoi(e) : 1;
+  }
+  return m;
 }
 
 static int gemm_force_bn() {      // PN_GEMM_BN: force the N tile of the non-streaming CTA-pair path (experiments)
@@ -911,6 +991,10 @@ extern "C" int pn_gemm(const pn_gemm_args* a, void* stream_v) {
     }
   }
   p.tiles_col = (a->N + BN - 1) / BN;
+  // weight-stationary schedule: 1x1 GEMMs with K = 320 (5 k-blocks, every ring has >= 5 stages) and enough column
+  // tiles and row tiles for the saved weight traffic to matter
+  p.bstat = (gemm_bstat_enabled() && !halo_mode && a->taps_h == 1 && a->taps_w == 1 && a->C == 5 * BK && p.tiles_col >= 3 &&
+             NCTA == 2 && tiles_m_1 >= 8 * sm_count() && p.tiles_col <= sm_count() / 8) ? 1 : 0;
 
   const uint64_t dimsA[4] = {(uint64_t)a->C, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
   const uint64_t strA[3] = {(uint64_t)sw, (uint64_t)sh, (uint64_t)sn};

@@ -38,9 +38,13 @@ class OpenAIWrapperControlLDM3D(IdentityWrapper):
         self._graph_sig = None
         self._static = None
 
-    def invalidate(self) -> None:
+    def invalidate(self, drop_graph: bool = True) -> None:
+        """Forget the prepared conditioning (next call re-runs the hint stem and the text K/V projections). The captured
+        graph only depends on shapes and on buffer addresses that survive a new conditioning, so a serving loop passes
+        drop_graph=False between samples and keeps replaying it."""
         self._cond_id = None
-        self._graph = None
+        if drop_graph:
+            self._graph = None
 
     @torch.no_grad()
     def prepare(self, c: dict) -> None:

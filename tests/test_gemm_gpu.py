@@ -76,6 +76,38 @@ def test_gemm_geglu(ops):
     _check(out, ref, tol=1e-2, name="geglu")
 
 
+@pytest.mark.parametrize("kind", ["fp32_res", "bf16", "geglu", "fp32_wide"])
+def test_gemm_weight_stationary_schedule(ops, kind):
+    """K = 320 with many row tiles takes the weight-stationary schedule (contiguous column-major tile ranges, the
+    weight tile resident in shared memory); M is not a multiple of the 256-row pair tile and the last unit's range
+    crosses a column-tile boundary."""
+    M, K = 8 * 148 * 128 + 333, 320
+    a = _rand((M, K), 40)
+    if kind == "geglu":
+        N = 2560
+        w = _rand((N, K), 41, K ** -0.5)
+        b = _rand((N,), 42, dtype=torch.float32)
+        out = ops.gemm(a, geglu_pack(w), bias=geglu_pack(b), geglu=True, out_dtype=torch.bfloat16)
+        torch.cuda.synchronize()
+        y = a.float() @ w.float().t() + b
+        _check(out, y[:, :N // 2] * F.gelu(y[:, N // 2:]), tol=1e-2, name="bstat geglu")
+    elif kind == "bf16":
+        N = 960
+        w = _rand((N, K), 43, K ** -0.5)
+        out = ops.gemm(a, w, out_dtype=torch.bfloat16)
+        torch.cuda.synchronize()
+        _check(out, a.float() @ w.float().t(), tol=1e-2, name="bstat bf16")
+    else:
+        N = 960 if kind == "fp32_wide" else 480
+        w = _rand((N, K), 44, K ** -0.5)
+        bias = _rand((N,), 45, dtype=torch.float32)
+        res = _rand((M, N), 46, dtype=torch.float32)
+        ref = a.float() @ w.float().t() + bias + res
+        out = ops.gemm(a, w, bias=bias, residual=res)
+        torch.cuda.synchronize()
+        _check(out, ref, name="bstat fp32+res")
+
+
 def test_gemm_strided_view(ops):
     M, C = 900, 320
     qkv = _rand((M, 3 * C), 13)
