@@ -54,7 +54,8 @@ struct FaParams {
   int kv_frame_div;            // kv frame = q frame / kv_frame_div
   int total_items;
   float scale_log2;            // softmax scale * log2(e)
-  int debug;                   // PN_ATTN_DEBUG (timing experiments): 1 = no softmax math, 2 = no MMA issue
+  int debug;                   // PN_ATTN_DEBUG (timing experiments): 1 = no softmax math, 2 = no MMA issue,
+                               // 4 = no exp2-phase turn taking between the two softmax groups
   __nv_bfloat16* out;
   long long out_ld;            // token stride of out (elements)
 };
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
     // The exp2 phase saturates the MUFU of all four schedulers; the two groups take turns in it (named barriers
     // 1 = "A may go", 2 = "B may go"), so one group's TMEM traffic, maxima and barrier waits hide behind the other's
     // exponentials instead of the two running in lock step. Group B hands A the first turn.
-    if (sl == 1) named_bar_arrive(1, 256);
+    if (sl == 1 && p.debug != 4) named_bar_arrive(1, 256);
     uint32_t n = 0;                  // blocks this group has processed (phase of s_full / pv_done)
     bool have_prev = false;
     int prev_ti = 0, prev_head = 0, prev_view = 0, prev_frame = 0;
@@ -283,6 +284,9 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
       const FaItem t = fa_decode(p, item);
       if (sl == 1 && !t.has_b) continue;
       float m_run = -INFINITY, l_run = 0.f;
+      // turn taking pays off when a tile has several key blocks (view attention: 583 vs 637 us at level 0); with a single
+      // block per tile (text: 77 keys) the hand-over only adds latency (84 vs 73 us)
+      const bool turns = t.has_b && t.nblk > 1 && p.debug != 4;
       for (int j = 0; j < t.nblk; ++j, ++n) {
         mbar_wait(&s_full[sl], n & 1);
         tc_fence_after();
@@ -321,7 +325,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
         const bool need = (j > 0) && __any_sync(0xffffffffu, upd);
         const f32x2 nm2 = f2_splat(-m_run);
         f32x2 rs2[2] = {0ull, 0ull};
-        if (t.has_b) named_bar_sync(1 + sl, 256);
+        if (turns) named_bar_sync(1 + sl, 256);
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) {
           if (ch < nchunk) {
@@ -346,7 +350,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
           const float rs = a0 + a1;
           // the hand-over must not be scheduled ahead of the exponentials it stands for: its thread count is made to
           // depend (vacuously — a row sum is never this NaN pattern) on the sum of all of them
-          if (t.has_b) named_bar_arrive(2 - sl, 256u + (__float_as_uint(rs) == 0x7fc0beefu ? 32u : 0u));
+          if (turns) named_bar_arrive(2 - sl, 256u + (__float_as_uint(rs) == 0x7fc0beefu ? 32u : 0u));
           l_run = l_run * alpha + rs;
         }
         // P_t / O_t may only be touched once the previous PV of this tile slot has retired
@@ -384,7 +388,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
       prev_ti = t.t0 + sl; prev_head = t.head; prev_view = t.view; prev_frame = t.frame;
       l_prev = l_run;
     }
-    if (sl == 0) named_bar_sync(1, 256);          // consume the turn that is still outstanding
+    if (sl == 0 && p.debug != 4) named_bar_sync(1, 256);          // consume the turn that is still outstanding
     if (have_prev) {
       mbar_wait(&pv_done[sl], (n & 1) ^ 1);
       tc_fence_after();

@@ -28,7 +28,7 @@ constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle atom row
 // warp 0 TMA, warp 1 MMA, warps 2.. epilogue: 8 warps for the fp32/residual mode (168 registers each), 12 for the
 // ALU-heavy bf16 / GEGLU modes (the register file is granted per 4-warp group: 16 warps x 128 registers)
 constexpr bool gemm_streaming(int mode) { return mode == 4 || mode == 5; }
-constexpr int gemm_threads(int mode) { return (mode == 0 || mode == 3 || mode == 6) ? 320 : gemm_streaming(mode) ? 352 : 448; }
+constexpr int gemm_threads(int mode) { return (mode == 0 || mode == 3 || mode == 6) ? 320 : gemm_streaming(mode) ? 352 : mode == 2 ? 576 : 448; }
 
 struct GemmParams {
   CUtensorMap mapA;
@@ -878,7 +878,8 @@ static int launch_gemm_mode(const GemmParams& p, cudaStream_t stream) {
 
 template <int BN, int STAGES, int NCTA>
 static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
-  if (p.geglu) return launch_gemm_mode<BN, STAGES, NCTA, 2>(p, stream);
+  // GEGLU runs 16 epilogue warps (its epilogue, not the k loop, is the long pole): one ring stage pays for their staging
+  if (p.geglu) return launch_gemm_mode<BN, (STAGES > 5 ? STAGES - 1 : STAGES), NCTA, 2>(p, stream);
   if (p.out_bf16) return launch_gemm_mode<BN, STAGES, NCTA, 1>(p, stream);
   if (p.residual2 != nullptr) return launch_gemm_mode<BN, STAGES, NCTA, 3>(p, stream);
   return launch_gemm_mode<BN, STAGES, NCTA, 0>(p, stream);

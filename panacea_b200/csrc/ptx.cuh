@@ -361,21 +361,6 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
-// erf by Abramowitz & Stegun 7.1.26 (|abs error| <= 1.5e-7 + MUFU rounding): 1 rcp + 1 ex2 + 7 FMA instead of the
-// ~30-instruction libdevice erff; used where the result is rounded to bf16 anyway (GEGLU epilogue).
-__device__ __forceinline__ float erf_fast(float x) {
-  const float ax = fabsf(x);
-  const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  const float r = 1.0f - poly * ex2_approx(-1.4426950408889634f * ax * ax);
-  return copysignf(r, x);
-}
-__device__ __forceinline__ float gelu_erf_fast(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f)); }
 
 // ---- packed fp32 pairs (sm_100 FFMA2/FMUL2/FADD2: two lanes of fp32 math per issue slot) ----
 typedef unsigned long long f32x2;
@@ -404,28 +389,28 @@ __device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
   return r;
 }
 
-// value * gelu_erf(gate) on two (value, gate) pairs at once. gelu(g) = g * Phi(g), Phi(g) = 1 - q for g >= 0 and q for
-// g < 0 with q = 0.5 * erfc(|g| / sqrt2) = 0.5 * poly(t) * exp(-g^2/2), t = 1 / (1 + p |g| / sqrt2)  (Abramowitz &
-// Stegun 7.1.26, |abs error of erf| <= 1.5e-7), hence  g * Phi(g) = 0.5 g + |g| (0.5 - q).
+// value * gelu_erf(gate) on two (value, gate) pairs at once. gelu(g) = g * Phi(g) with Phi(g) = q for g < 0 and 1 - q
+// for g >= 0, q = Phi(-|g|) = 0.5 * erfc(|g| / sqrt2), hence  g * Phi(g) = 0.5 g + |g| (0.5 - q).
+// q = 0.5 * 2^(-t Q(t)), t = min(|g|, 7): Q is a degree-6 polynomial fitted (weighted minimax, tools/fit_erfc.py) to
+// -log2(erfc(t / sqrt2)) / t on [0, 7]; |q error| <= 8.3e-8 in fp32 arithmetic, i.e. an erf error of 1.7e-7 — the
+// same class as Abramowitz & Stegun 7.1.26 — with ONE MUFU op per element instead of two (rcp + ex2): the MUFU was
+// the busiest unit of the GEGLU epilogue.
 __device__ __forceinline__ f32x2 geglu_f32x2(f32x2 value, f32x2 gate) {
   const f32x2 ag = gate & 0x7FFFFFFF7FFFFFFFull;
-  const f32x2 d = f2_fma(ag, f2_splat(0.3275911f * 0.70710678118654752f), f2_splat(1.0f));
-  float d0, d1;
-  f2_unpack(d, d0, d1);
-  const f32x2 t = f2_pack(rcp_approx(d0), rcp_approx(d1));
-  // exp(-g^2/2) = 2^(-(g * sqrt(log2(e)/2))^2); the negation rides on the MUFU operand
-  const f32x2 sg = f2_mul(gate, f2_splat(0.84932180028801905f));
-  const f32x2 m = f2_mul(sg, sg);
-  float m0, m1;
-  f2_unpack(m, m0, m1);
-  const f32x2 e = f2_pack(ex2_approx(-m0), ex2_approx(-m1));
-  // -q / e = -0.5 * (a1 t + ... + a5 t^5)
-  f32x2 poly = f2_fma(f2_splat(-0.5f * 1.061405429f), t, f2_splat(-0.5f * -1.453152027f));
-  poly = f2_fma(poly, t, f2_splat(-0.5f * 1.421413741f));
-  poly = f2_fma(poly, t, f2_splat(-0.5f * -0.284496736f));
-  poly = f2_fma(poly, t, f2_splat(-0.5f * 0.254829592f));
-  poly = f2_mul(poly, t);
-  const f32x2 r = f2_fma(poly, e, f2_splat(0.5f));                              // 0.5 - q
+  float a0, a1;
+  f2_unpack(ag, a0, a1);
+  const f32x2 t = f2_pack(fminf(a0, 7.0f), fminf(a1, 7.0f));
+  f32x2 qp = f2_fma(f2_splat(-8.857143257e-06f), t, f2_splat(5.7686524087e-05f));
+  qp = f2_fma(qp, t, f2_splat(4.070131981e-04f));
+  qp = f2_fma(qp, t, f2_splat(-7.363174111e-03f));
+  qp = f2_fma(qp, t, f2_splat(5.2666641772e-02f));
+  qp = f2_fma(qp, t, f2_splat(4.591643214e-01f));
+  qp = f2_fma(qp, t, f2_splat(1.1511088610f));
+  const f32x2 u = f2_mul(qp, t);
+  float u0, u1;
+  f2_unpack(u, u0, u1);
+  const f32x2 e = f2_pack(ex2_approx(-u0), ex2_approx(-u1));                    // erfc(t / sqrt2); negation on the MUFU operand
+  const f32x2 r = f2_fma(e, f2_splat(-0.5f), f2_splat(0.5f));                   // 0.5 - q
   const f32x2 gelu = f2_fma(gate, f2_splat(0.5f), f2_mul(ag, r));
   return f2_mul(value, gelu);
 }
