@@ -249,6 +249,10 @@ class Engine:
         y = ops.gemm(o.view(-1, C), W[t + ".attn2.o.w"], bias=W[t + ".attn2.o.b"], residual=y, out=y)
         n3 = ops.layernorm(y, W[t + ".norm3.g"], W[t + ".norm3.b"])
         ff = ops.gemm(n3, W[t + ".ff1.w"], bias=W[t + ".ff1.b"], geglu=True, out_dtype=dt)
+        # the block's output is only ever consumed as the bf16 operand of proj_out: emit it in that form directly
+        # (saves the fp32 write, the cast kernel's fp32 read and one launch per transformer block)
+        if self.dt == torch.bfloat16:
+            return ops.gemm(ff, W[t + ".ff2.w"], bias=W[t + ".ff2.b"], residual=y, out_dtype=torch.bfloat16)
         return ops.gemm(ff, W[t + ".ff2.w"], bias=W[t + ".ff2.b"], residual=y, out=y)
 
     def _stt(self, W, st: Stage, x):
@@ -267,7 +271,7 @@ class Engine:
                 y = ops.gemm(a.view(-1, C), W[f"{k}.proj_in{br}.w"], bias=W[f"{k}.proj_in{br}.b"])
             t = f"{k}.transformer_blocks{br}.0"
             y = self._transformer(W, t, y, st.heads, mode, geom, self.cond["kv"][(id(W), t)])
-            yb = self._to_operand(y)
+            yb = y if y.dtype == self.dt else self._to_operand(y)
             x = ops.gemm(yb, W[f"{k}.proj_out{br}.w"], bias=W[f"{k}.proj_out{br}.b"], residual=x, out=x).view(Fr, H, Wd, C)
         return x
 

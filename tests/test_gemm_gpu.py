@@ -108,6 +108,18 @@ def test_gemm_weight_stationary_schedule(ops, kind):
         _check(out, ref, name="bstat fp32+res")
 
 
+@pytest.mark.parametrize("M,N,K", [(3000, 320, 1280), (700, 1280, 5120)])
+def test_gemm_bf16_out_with_fp32_residual(ops, M, N, K):
+    """Last GEMM of a transformer block (ff2 + residual) emitting the bf16 operand of proj_out directly."""
+    a = _rand((M, K), 50); w = _rand((N, K), 51, K ** -0.5)
+    bias = _rand((N,), 52, dtype=torch.float32)
+    res = _rand((M, N), 53, dtype=torch.float32)
+    out = ops.gemm(a, w, bias=bias, residual=res, out_dtype=torch.bfloat16)
+    torch.cuda.synchronize()
+    assert out.dtype == torch.bfloat16
+    _check(out, a.float() @ w.float().t() + bias + res, tol=1e-2, name="bf16 out + fp32 residual")
+
+
 def test_gemm_strided_view(ops):
     M, C = 900, 320
     qkv = _rand((M, 3 * C), 13)
