@@ -89,6 +89,12 @@ struct GemmSmem {
 //       6 = 3x3 conv with a HALOED A tile: the 9 taps of one 64-channel chunk are 9 row-shifted UMMA views of ONE
 //           (16+2)x(8+2)-pixel tile in shared memory, so the activations cross the L2->SM fabric once instead of 9
 //           times (the L2-bound N=160 tile of the level-0/1 convs); fp32 store through the generic epilogue.
+// PN_GEMM_DEBUG=5: cycle accounting of CTA 0's warp roles (tools/gemm_probe3.py prints it)
+//  [0] issuer total  [1] issuer waiting accumulator  [2] issuer waiting operands  [3] tiles
+//  [4] producer total [5] producer waiting free slots
+//  [6] epilogue warp 2 total [7] waiting tmem_full [8] waiting staging chunk  [9] store warp waiting chunks [10] waiting smem reads
+__device__ unsigned long long g_gemm_dbg[16];
+
 template <int BN, int STAGES, int NCTA, int MODE>
 __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using S = GemmSmem<BN, STAGES, NCTA, MODE>;
@@ -292,6 +298,8 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
     bool first = true;
     int cur_col = -1;
     uint32_t bgen = 0;                            // weight-stationary: weight tiles loaded so far
+    const bool dbg = p.debug == 5 && blockIdx.x == 0;
+    long long d_t0 = dbg ? clock64() : 0, d_wait = 0;
     for (int ti = 0, tile = t_begin; ti < t_count; ++ti, tile += t_step) {
       const int tcol = tile_col(tile);
       int tm = tile_mu(tile) * NCTA + (int)cta_rank;
@@ -321,7 +329,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
       int kc = 0, dx = -p.pad_w, dy = -p.pad_h;   // k-block -> (tap row, tap column, channel chunk), kept incrementally
       for (int kb = 0; kb < num_k_blocks; ++kb) {
         if (!(p.debug == 1 && !(first && kb < STAGES))) {   // experiment 1: the ring is filled once, never again
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          { const long long w0 = dbg ? clock64() : 0; mbar_wait(&empty_bar[stage], phase ^ 1); if (dbg) d_wait += clock64() - w0; }
           if (elect_one()) {
             uint8_t* sA = stage_base + stage * S::STAGE_BYTES;
             uint8_t* sB = sA + S::A_BYTES;
@@ -345,6 +353,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
       }
       first = false;
     }
+    if (dbg && lane == 0) { g_gemm_dbg[4] = (unsigned long long)(clock64() - d_t0); g_gemm_dbg[5] = (unsigned long long)d_wait; }
   } else if (warp == 1) {
     // ===================== UMMA issuer (leader CTA of a pair only) =====================
     // Kept deliberately plain (runtime ring position, descriptors = uniform base + stage * step + k): in this form ptxas
@@ -362,17 +371,21 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
       bool first = true;
       int cur_col = -1;
       uint32_t bgen = 0;
+      const bool dbg = p.debug == 5 && blockIdx.x == 0;
+      long long d_t0 = dbg ? clock64() : 0, d_acc = 0, d_full = 0;
       for (int ti = 0, tile = t_begin; ti < t_count; ++ti, tile += t_step) {
         const bool bstat = MODE != 6 && p.bstat;
         const int tcol = tile_col(tile);
         const bool new_b = bstat && tcol != cur_col;              // first tile on a freshly loaded weight tile
         if (new_b) { cur_col = tcol; ++bgen; }
         const bool last_b = bstat && (ti + 1 == t_count || tile_col(tile + t_step) != tcol);
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        { const long long w0 = dbg ? clock64() : 0; mbar_wait(&tmem_empty[acc], acc_phase ^ 1); if (dbg) d_acc += clock64() - w0; }
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
+          const long long w1 = dbg ? clock64() : 0;
           if (!(p.debug == 1 && !(first && kb < STAGES))) mbar_wait(&full_bar[stage], phase);
+          if (dbg) d_full += clock64() - w1;
           if (new_b) mbar_wait(&b_full[kb], (bgen - 1) & 1);
           tc_fence_after();
           if (elect_one()) {
@@ -402,6 +415,10 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
         first = false;
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+      if (dbg && lane == 0) {
+        g_gemm_dbg[0] = (unsigned long long)(clock64() - d_t0); g_gemm_dbg[1] = (unsigned long long)d_acc;
+        g_gemm_dbg[2] = (unsigned long long)d_full; g_gemm_dbg[3] = (unsigned long long)t_count;
+      }
     }
   } else if (gemm_streaming(MODE) && warp == 10) {
     // ===================== MODE 4: residual-load / output-store warp =====================
@@ -409,6 +426,8 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
       constexpr int NCH = BN / 32;
       bool first = true;
       int it = 0;
+      const bool dbg = p.debug == 5 && blockIdx.x == 0;
+      long long d_c = 0, d_r = 0;
       for (int ti = 0, tile = t_begin; ti < t_count; ++ti, tile += t_step, ++it) {
         const int tcol = tile_col(tile);
         int tm = tile_mu(tile) * NCTA + (int)cta_rank;
@@ -441,13 +460,13 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
         // ITS group has been read out of shared memory — waiting per store serialised the store warp
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
-          mbar_wait(&c_ready[c], (uint32_t)(it & 1));
+          { const long long w0 = dbg ? clock64() : 0; mbar_wait(&c_ready[c], (uint32_t)(it & 1)); if (dbg) d_c += clock64() - w0; }
           if (p.debug != 4) tma_store_2d(&p.mapOut, staging + c * S::RCHUNK_BYTES, n0 + c * 32, m0);
           tma_store_commit();
         }
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
-          tma_store_wait_read_le(NCH - 1 - c);         // groups complete in order: chunk c has left shared memory
+          { const long long w0 = dbg ? clock64() : 0; tma_store_wait_read_le(NCH - 1 - c); if (dbg) d_r += clock64() - w0; }   // groups complete in order
           if (has_next) {
             if (p.has_res) {
               mbar_arrive_expect_tx(&r_full[c], S::RCHUNK_BYTES);
@@ -459,6 +478,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
         }
       }
       tma_store_wait_all();
+      if (dbg) { g_gemm_dbg[9] = (unsigned long long)d_c; g_gemm_dbg[10] = (unsigned long long)d_r; }
     }
   } else if (gemm_streaming(MODE)) {
     // ===================== MODE 4/5: epilogue warps 2..9, thread == tile row =====================
@@ -471,6 +491,8 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
     const uint32_t te_addr0 = (NCTA == 2) ? mapa_shared(smem_u32(&tmem_empty[0]), 0) : smem_u32(&tmem_empty[0]);
     int acc = 0, it = 0;
     uint32_t acc_phase = 0;
+    const bool dbg = p.debug == 5 && blockIdx.x == 0 && warp == 2;
+    long long d_t0 = dbg ? clock64() : 0, d_tf = 0, d_rf = 0;
     for (int ti = 0, tile = t_begin; ti < t_count; ++ti, tile += t_step, ++it) {
       const int tcol = tile_col(tile);
       int tm = tile_mu(tile) * NCTA + (int)cta_rank;
@@ -478,7 +500,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
       const int thi = tm % p.tiles_h; tm /= p.tiles_h;
       const long long grow = (long long)(tm * p.H + thi) * p.W + twi * p.tw + r;
       const int n_base = tcol * BN;
-      mbar_wait(&tmem_full[acc], acc_phase);
+      { const long long w0 = dbg ? clock64() : 0; mbar_wait(&tmem_full[acc], acc_phase); if (dbg) d_tf += clock64() - w0; }
       tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t(lane_grp * 32) << 16) + acc * BN;
 #pragma unroll
@@ -515,7 +537,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
               f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
             }
           }
-          mbar_wait(&r_full[c], (uint32_t)(it & 1));
+          { const long long w0 = dbg ? clock64() : 0; mbar_wait(&r_full[c], (uint32_t)(it & 1)); if (dbg) d_rf += clock64() - w0; }
           if (p.debug == 3) {
           } else if (MODE == 5) {
             // 32 bf16 = 64 B per row; TMA SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3
@@ -545,6 +567,9 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
         }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (dbg && lane == 0) {
+      g_gemm_dbg[6] = (unsigned long long)(clock64() - d_t0); g_gemm_dbg[7] = (unsigned long long)d_tf; g_gemm_dbg[8] = (unsigned long long)d_rf;
     }
   } else {
     // ===================== epilogue warps: TMEM lane quarter = warp & 3, chunk residue = (warp - 2) / 4 ==========
@@ -1029,4 +1054,11 @@ extern "C" int pn_gemm(const pn_gemm_args* a, void* stream_v) {
     case 64: return launch_gemm<64, 8, 1>(p, stream);
     default: return launch_gemm<32, 8, 1>(p, stream);
   }
+}
+
+// diagnostics (not part of the product ABI): role cycle counters of the last pn_gemm launch made with PN_GEMM_DEBUG=5
+extern "C" int pn_debug_gemm_counters(unsigned long long* out16) {
+  PN_CHECK_CUDA(cudaDeviceSynchronize());
+  PN_CHECK_CUDA(cudaMemcpyFromSymbol(out16, pn::g_gemm_dbg, sizeof(unsigned long long) * 16));
+  return PN_OK;
 }

@@ -1,5 +1,5 @@
 """Epilogue/mainloop decomposition of the K=320 transformer GEMMs at the L0 shape (PN_GEMM_DEBUG = 0..4)."""
-import os, sys
+import ctypes, os, sys
 from pathlib import Path
 import torch
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
@@ -23,3 +23,11 @@ rows = [
 for name, fn, fl in rows:
     t = timeit(fn)
     print(f"[{tag}] {name:18s} {t*1e6:8.1f} us {fl/t/1e12:7.1f} TF/s")
+    if os.environ.get("PN_GEMM_DEBUG") == "5":
+        c = (ctypes.c_ulonglong * 16)()
+        ops.lib.pn_debug_gemm_counters(c)
+        v = [int(x) for x in c]
+        nt = max(v[3], 1)
+        print(f"      per tile (CTA 0, {v[3]} tiles): issuer {v[0]/nt:.0f} cyc (wait accumulator {v[1]/nt:.0f}, wait operands {v[2]/nt:.0f}); "
+              f"producer {v[4]/nt:.0f} (wait slots {v[5]/nt:.0f}); epilogue warp {v[6]/nt:.0f} (wait tmem_full {v[7]/nt:.0f}, "
+              f"wait chunk {v[8]/nt:.0f}); store warp waits: chunks {v[9]/nt:.0f}, smem reads {v[10]/nt:.0f}")
