@@ -26,6 +26,8 @@ NVCC_FLAGS = [
     "--expt-relaxed-constexpr",
     "-I", str(INCLUDE),
 ]
+if os.environ.get("PN_GEMM_ROLE_TIMERS") == "1":      # diagnostics build: per-role cycle counters in gemm_tc_kernel
+    NVCC_FLAGS.append("-DPN_GEMM_ROLE_TIMERS")
 
 
 def _sources() -> list[Path]:

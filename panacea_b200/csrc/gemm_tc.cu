@@ -89,11 +89,17 @@ struct GemmSmem {
 //       6 = 3x3 conv with a HALOED A tile: the 9 taps of one 64-channel chunk are 9 row-shifted UMMA views of ONE
 //           (16+2)x(8+2)-pixel tile in shared memory, so the activations cross the L2->SM fabric once instead of 9
 //           times (the L2-bound N=160 tile of the level-0/1 convs); fp32 store through the generic epilogue.
-// PN_GEMM_DEBUG=5: cycle accounting of CTA 0's warp roles (tools/gemm_probe3.py prints it)
+// Role cycle accounting of CTA 0 (tools/gemm_probe3.py prints it): compiled in only with -DPN_GEMM_ROLE_TIMERS
+// (PN_GEMM_ROLE_TIMERS=1 python -m panacea_b200.build --force), then enabled at run time by PN_GEMM_DEBUG=5
 //  [0] issuer total  [1] issuer waiting accumulator  [2] issuer waiting operands  [3] tiles
 //  [4] producer total [5] producer waiting free slots
 //  [6] epilogue warp 2 total [7] waiting tmem_full [8] waiting staging chunk  [9] store warp waiting chunks [10] waiting smem reads
 __device__ unsigned long long g_gemm_dbg[16];
+#ifdef PN_GEMM_ROLE_TIMERS
+constexpr bool kRoleTimers = true;
+#else
+constexpr bool kRoleTimers = false;
+#endif
 
 template <int BN, int STAGES, int NCTA, int MODE>
 __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
@@ -298,7 +304,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
     bool first = true;
     int cur_col = -1;
     uint32_t bgen = 0;                            // weight-stationary: weight tiles loaded so far
-    const bool dbg = p.debug == 5 && blockIdx.x == 0;
+    const bool dbg = kRoleTimers && p.debug == 5 && blockIdx.x == 0;
     long long d_t0 = dbg ? clock64() : 0, d_wait = 0;
     for (int ti = 0, tile = t_begin; ti < t_count; ++ti, tile += t_step) {
       const int tcol = tile_col(tile);
@@ -371,7 +377,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
       bool first = true;
       int cur_col = -1;
       uint32_t bgen = 0;
-      const bool dbg = p.debug == 5 && blockIdx.x == 0;
+      const bool dbg = kRoleTimers && p.debug == 5 && blockIdx.x == 0;
       long long d_t0 = dbg ? clock64() : 0, d_acc = 0, d_full = 0;
       for (int ti = 0, tile = t_begin; ti < t_count; ++ti, tile += t_step) {
         const bool bstat = MODE != 6 && p.bstat;
@@ -426,7 +432,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
       constexpr int NCH = BN / 32;
       bool first = true;
       int it = 0;
-      const bool dbg = p.debug == 5 && blockIdx.x == 0;
+      const bool dbg = kRoleTimers && p.debug == 5 && blockIdx.x == 0;
       long long d_c = 0, d_r = 0;
       for (int ti = 0, tile = t_begin; ti < t_count; ++ti, tile += t_step, ++it) {
         const int tcol = tile_col(tile);
@@ -491,7 +497,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
     const uint32_t te_addr0 = (NCTA == 2) ? mapa_shared(smem_u32(&tmem_empty[0]), 0) : smem_u32(&tmem_empty[0]);
     int acc = 0, it = 0;
     uint32_t acc_phase = 0;
-    const bool dbg = p.debug == 5 && blockIdx.x == 0 && warp == 2;
+    const bool dbg = kRoleTimers && p.debug == 5 && blockIdx.x == 0 && warp == 2;
     long long d_t0 = dbg ? clock64() : 0, d_tf = 0, d_rf = 0;
     for (int ti = 0, tile = t_begin; ti < t_count; ++ti, tile += t_step, ++it) {
       const int tcol = tile_col(tile);

@@ -1,4 +1,5 @@
-"""Epilogue/mainloop decomposition of the K=320 transformer GEMMs at the L0 shape (PN_GEMM_DEBUG = 0..4)."""
+"""Epilogue/mainloop decomposition of the K=320 transformer GEMMs at the L0 shape (PN_GEMM_DEBUG = 0..4), and the
+per-role cycle accounting of CTA 0 (PN_GEMM_DEBUG=5 on a library built with PN_GEMM_ROLE_TIMERS=1)."""
 import ctypes, os, sys
 from pathlib import Path
 import torch
