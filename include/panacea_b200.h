@@ -97,7 +97,8 @@ typedef struct pn_attn_args {
 int pn_attention(const pn_attn_args* args, void* stream);
 
 /* Temporal self-attention over T <= 16 frames per pixel (attention.py:1116-1125 -> :229-291, context=None).
- * q/k/v/out bf16 [batch, T, pixels, ld]; one (batch, pixel, head) sequence per warp, fp32 softmax. */
+ * q/k/v/out bf16 [batch, T, pixels, ld]; one (batch, pixel, head) sequence per warp (warp-level bf16 MMAs, fp32
+ * softmax); ld and out_ld multiples of 8. */
 int pn_attention_temporal(const void* q, const void* k, const void* v, void* out, int64_t batch, int64_t T,
                           int64_t pixels, int32_t heads, int32_t head_dim, int64_t ld, int64_t out_ld, float scale,
                           void* stream);

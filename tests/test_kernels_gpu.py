@@ -126,7 +126,8 @@ def test_attention_text(ops, b, Nq, heads, Nk):
     _close(out, ref, 2e-2, "attention_text")
 
 
-@pytest.mark.parametrize("b,T,P,heads", [(2, 8, 100, 2), (1, 8, 2688, 5), (2, 4, 33, 1), (1, 16, 64, 2), (1, 1, 10, 1)])
+@pytest.mark.parametrize("b,T,P,heads", [(2, 8, 100, 2), (1, 8, 2688, 5), (2, 4, 33, 1), (1, 16, 64, 2), (1, 1, 10, 1), (1, 5, 40, 2),
+                                           (2, 12, 17, 1)])
 def test_attention_temporal(ops, b, T, P, heads):
     C = heads * 64
     qkv = _rand((b, T, P, 3 * C), 14, 1.0, torch.bfloat16)
