@@ -118,3 +118,27 @@ def test_install_as_sgm_resolves_reference_targets():
         for k in [k for k in sys.modules if k == "sgm" or k.startswith("sgm.")]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+def test_geglu_pack_is_the_layout_the_epilogue_contract_states():
+    """include/panacea_b200.h: GEGLU columns come in blocks of 32 = 16 value columns then the 16 gate columns of the same
+    outputs; packing the reference's [value rows | gate rows] projection (attention.py:94-99) and applying the blockwise
+    rule must reproduce value * gelu(gate)."""
+    import torch.nn.functional as F
+    from panacea_b200.ops import geglu_pack
+    g = torch.Generator().manual_seed(5)
+    inner, C, M = 64, 48, 7
+    w = torch.randn(2 * inner, C, generator=g)
+    b = torch.randn(2 * inner, generator=g)
+    x = torch.randn(M, C, generator=g)
+    wp, bp = geglu_pack(w), geglu_pack(b)
+    assert wp.shape == w.shape and bp.shape == b.shape
+    # block structure: rows [32k, 32k+16) are value rows 16k.., rows [32k+16, 32k+32) the matching gate rows
+    assert torch.equal(wp[0:16], w[0:16]) and torch.equal(wp[16:32], w[inner:inner + 16])
+    assert torch.equal(wp[32:48], w[16:32]) and torch.equal(wp[48:64], w[inner + 16:inner + 32])
+    y = x @ w.t() + b
+    ref = y[:, :inner] * F.gelu(y[:, inner:])
+    got = TorchRefOps().gemm(x, wp, bias=bp, geglu=True, out_dtype=torch.float32)
+    torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-5)
+    with pytest.raises(ValueError):
+        geglu_pack(torch.zeros(40, 4))
