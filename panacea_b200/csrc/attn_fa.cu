@@ -38,6 +38,12 @@ constexpr int FA_SMEM_BAR = FA_SMEM_V + FA_STAGES * FA_TILE_BYTES;
 constexpr int FA_SMEM_TOTAL = FA_SMEM_BAR + 512 + 1024;
 // tensor memory columns: S_A S_B (fp32, 128 each) | P_A P_B (bf16 pairs, 64 each) | O_A O_B (fp32, 64 each)
 constexpr uint32_t FA_TM_S = 0, FA_TM_P = 256, FA_TM_O = 384;
+// PN_ATTN_DEBUG timing experiments exist only in diagnostics builds (-DPN_GEMM_ROLE_TIMERS, see build.py)
+#ifdef PN_GEMM_ROLE_TIMERS
+constexpr bool kFaExperiments = true;
+#else
+constexpr bool kFaExperiments = false;
+#endif
 constexpr float FA_LAZY_LOG2 = 8.0f;              // raise the reference maximum only when it grew by more than 2^8
 
 struct FaParams {
@@ -103,6 +109,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int dbgmode = kFaExperiments ? p.debug : 0;
 
   // zero Q/K/V staging once: rows a TMA box does not cover (kv_rows..kv_n) must read as 0, never as stale NaNs
   {
@@ -191,7 +198,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
               const uint32_t tO = tmem_base + FA_TM_O + sl * 64, tP = tmem_base + FA_TM_P + sl * 64;
 #pragma unroll
               for (int k = 0; k < 8; ++k)   // 16 keys per step: 8 packed columns of P, 16 rows (128 B each) of V
-                if (k < ksteps_pv && p.debug != 2) umma_f16_ts(tO, tP + 8 * k, dV + 128 * k, idesc_pv, (pend_j > 0 || k > 0) ? 1u : 0u);
+                if (k < ksteps_pv && dbgmode != 2) umma_f16_ts(tO, tP + 8 * k, dV + 128 * k, idesc_pv, (pend_j > 0 || k > 0) ? 1u : 0u);
               umma_commit(&pv_done[sl]);
               if (sl == 1 || !pend_b) umma_commit(&kv_empty[st]);
             }
@@ -215,7 +222,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
               tc_fence_after();
               if (elect_one()) {
                 const uint64_t dQ = dQ0 + TILE_STEP * (qb * 2 + sl);
-                if (p.debug != 2) {
+                if (dbgmode != 2) {
 #pragma unroll
                   for (int k = 0; k < FA_D / 16; ++k)
                     umma_f16_ss(tmem_base + FA_TM_S + sl * 128, dQ + 2 * k, dK + 2 * k, idesc_s, k > 0 ? 1u : 0u);
@@ -275,7 +282,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
     // The exp2 phase saturates the MUFU of all four schedulers; the two groups take turns in it (named barriers
     // 1 = "A may go", 2 = "B may go"), so one group's TMEM traffic, maxima and barrier waits hide behind the other's
     // exponentials instead of the two running in lock step. Group B hands A the first turn.
-    if (sl == 1 && p.debug != 4) named_bar_arrive(1, 256);
+    if (sl == 1 && dbgmode != 4) named_bar_arrive(1, 256);
     uint32_t n = 0;                  // blocks this group has processed (phase of s_full / pv_done)
     bool have_prev = false;
     int prev_ti = 0, prev_head = 0, prev_view = 0, prev_frame = 0;
@@ -286,7 +293,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
       float m_run = -INFINITY, l_run = 0.f;
       // turn taking pays off when a tile has several key blocks (view attention: 583 vs 637 us at level 0); with a single
       // block per tile (text: 77 keys) the hand-over only adds latency (84 vs 73 us)
-      const bool turns = t.has_b && t.nblk > 1 && p.debug != 4;
+      const bool turns = t.has_b && t.nblk > 1 && dbgmode != 4;
       for (int j = 0; j < t.nblk; ++j, ++n) {
         mbar_wait(&s_full[sl], n & 1);
         tc_fence_after();
@@ -298,7 +305,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_free[sl]);      // the tensor core may overwrite S_t with the next block
-        if (p.debug == 1) {
+        if (dbgmode == 1) {
           mbar_wait(&pv_done[sl], (n & 1) ^ 1);
           tc_fence_after();
           if (j == 0 && have_prev) epilogue(prev_ti, prev_head, prev_view, prev_frame, l_prev);
@@ -388,7 +395,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
       prev_ti = t.t0 + sl; prev_head = t.head; prev_view = t.view; prev_frame = t.frame;
       l_prev = l_run;
     }
-    if (sl == 0 && p.debug != 4) named_bar_sync(1, 256);          // consume the turn that is still outstanding
+    if (sl == 0 && dbgmode != 4) named_bar_sync(1, 256);          // consume the turn that is still outstanding
     if (have_prev) {
       mbar_wait(&pv_done[sl], (n & 1) ^ 1);
       tc_fence_after();

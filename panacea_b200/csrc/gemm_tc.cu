@@ -100,6 +100,10 @@ constexpr bool kRoleTimers = true;
 #else
 constexpr bool kRoleTimers = false;
 #endif
+// The PN_GEMM_DEBUG timing experiments (1-5) cost a constant-bank load, a compare and a branch per k-block in the two
+// single-warp loops that pace the short-K GEMMs: they exist only in diagnostics builds
+// (PN_GEMM_ROLE_TIMERS=1 python -m panacea_b200.build --force); the product build folds them away.
+constexpr bool kExperiments = kRoleTimers;
 
 template <int BN, int STAGES, int NCTA, int MODE>
 __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
@@ -125,6 +129,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int dbgmode = kExperiments ? p.debug : 0;
   // NCTA == 2: the two CTAs of a cluster form a UMMA pair (cta_group::2). Each CTA owns 128 rows of a 256-row
   // tile (its own A stage and TMEM lanes) and stages half of the N tile's weight rows; the leader (rank 0)
   // issues the MMAs for both, and the weights cross the L2->SM fabric once per pair instead of once per CTA.
@@ -304,7 +309,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
     bool first = true;
     int cur_col = -1;
     uint32_t bgen = 0;                            // weight-stationary: weight tiles loaded so far
-    const bool dbg = kRoleTimers && p.debug == 5 && blockIdx.x == 0;
+    const bool dbg = kRoleTimers && dbgmode == 5 && blockIdx.x == 0;
     long long d_t0 = dbg ? clock64() : 0, d_wait = 0;
     for (int ti = 0, tile = t_begin; ti < t_count; ++ti, tile += t_step) {
       const int tcol = tile_col(tile);
@@ -334,7 +339,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
       }
       int kc = 0, dx = -p.pad_w, dy = -p.pad_h;   // k-block -> (tap row, tap column, channel chunk), kept incrementally
       for (int kb = 0; kb < num_k_blocks; ++kb) {
-        if (!(p.debug == 1 && !(first && kb < STAGES))) {   // experiment 1: the ring is filled once, never again
+        if (!(dbgmode == 1 && !(first && kb < STAGES))) {   // experiment 1: the ring is filled once, never again
           { const long long w0 = dbg ? clock64() : 0; mbar_wait(&empty_bar[stage], phase ^ 1); if (dbg) d_wait += clock64() - w0; }
           if (elect_one()) {
             uint8_t* sA = stage_base + stage * S::STAGE_BYTES;
@@ -377,7 +382,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
       bool first = true;
       int cur_col = -1;
       uint32_t bgen = 0;
-      const bool dbg = kRoleTimers && p.debug == 5 && blockIdx.x == 0;
+      const bool dbg = kRoleTimers && dbgmode == 5 && blockIdx.x == 0;
       long long d_t0 = dbg ? clock64() : 0, d_acc = 0, d_full = 0;
       for (int ti = 0, tile = t_begin; ti < t_count; ++ti, tile += t_step) {
         const bool bstat = MODE != 6 && p.bstat;
@@ -390,14 +395,14 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           const long long w1 = dbg ? clock64() : 0;
-          if (!(p.debug == 1 && !(first && kb < STAGES))) mbar_wait(&full_bar[stage], phase);
+          if (!(dbgmode == 1 && !(first && kb < STAGES))) mbar_wait(&full_bar[stage], phase);
           if (dbg) d_full += clock64() - w1;
           if (new_b) mbar_wait(&b_full[kb], (bgen - 1) & 1);
           tc_fence_after();
           if (elect_one()) {
             const uint64_t da = descA0 + STAGE_STEP * stage;
             const uint64_t db = descB0 + STAGE_STEP * (bstat ? kb : stage);
-            if (p.debug != 2) {
+            if (dbgmode != 2) {
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) {
                 if (NCTA == 2) umma_f16_ss_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
@@ -432,7 +437,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
       constexpr int NCH = BN / 32;
       bool first = true;
       int it = 0;
-      const bool dbg = kRoleTimers && p.debug == 5 && blockIdx.x == 0;
+      const bool dbg = kRoleTimers && dbgmode == 5 && blockIdx.x == 0;
       long long d_c = 0, d_r = 0;
       for (int ti = 0, tile = t_begin; ti < t_count; ++ti, tile += t_step, ++it) {
         const int tcol = tile_col(tile);
@@ -467,7 +472,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           { const long long w0 = dbg ? clock64() : 0; mbar_wait(&c_ready[c], (uint32_t)(it & 1)); if (dbg) d_c += clock64() - w0; }
-          if (p.debug != 4) tma_store_2d(&p.mapOut, staging + c * S::RCHUNK_BYTES, n0 + c * 32, m0);
+          if (dbgmode != 4) tma_store_2d(&p.mapOut, staging + c * S::RCHUNK_BYTES, n0 + c * 32, m0);
           tma_store_commit();
         }
 #pragma unroll
@@ -497,7 +502,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
     const uint32_t te_addr0 = (NCTA == 2) ? mapa_shared(smem_u32(&tmem_empty[0]), 0) : smem_u32(&tmem_empty[0]);
     int acc = 0, it = 0;
     uint32_t acc_phase = 0;
-    const bool dbg = kRoleTimers && p.debug == 5 && blockIdx.x == 0 && warp == 2;
+    const bool dbg = kRoleTimers && dbgmode == 5 && blockIdx.x == 0 && warp == 2;
     long long d_t0 = dbg ? clock64() : 0, d_tf = 0, d_rf = 0;
     for (int ti = 0, tile = t_begin; ti < t_count; ++ti, tile += t_step, ++it) {
       const int tcol = tile_col(tile);
@@ -544,7 +549,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
             }
           }
           { const long long w0 = dbg ? clock64() : 0; mbar_wait(&r_full[c], (uint32_t)(it & 1)); if (dbg) d_rf += clock64() - w0; }
-          if (p.debug == 3) {
+          if (dbgmode == 3) {
           } else if (MODE == 5) {
             // 32 bf16 = 64 B per row; TMA SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3
             uint8_t* rowp = staging + c * S::RCHUNK_BYTES + r * 64;
@@ -665,7 +670,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
             __syncwarp();
             if (lane == 0) release_acc(acc);
           }
-          if (p.debug == 3) continue;
+          if (dbgmode == 3) continue;
           const int n0 = n_base + c * 32;
           float f[32];
 #pragma unroll
@@ -710,7 +715,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
               const int rr = i * 16 + (lane >> 1);
               const int ch = lane & 1;
               const int grow = my_rowmap[rr];
-              if (grow >= 0 && no0 + ch * 8 < p.N / 2 && p.debug != 4) {
+              if (grow >= 0 && no0 + ch * 8 < p.N / 2 && dbgmode != 4) {
                 const uint4 val = *reinterpret_cast<const uint4*>(my_stage + rr * 32 + ch * 16);
                 *reinterpret_cast<uint4*>(out + (long long)grow * p.ldo + no0 + ch * 8) = val;
               }
@@ -731,7 +736,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
               const int rr = i * 8 + (lane >> 2);
               const int ch = lane & 3;
               const int grow = my_rowmap[rr];
-              if (grow >= 0 && n0 + ch * 8 < p.N && p.debug != 4) {
+              if (grow >= 0 && n0 + ch * 8 < p.N && dbgmode != 4) {
                 const int sw = ch ^ ((rr >> 1) & 3);
                 uint4 val = *reinterpret_cast<const uint4*>(my_stage + rr * 64 + sw * 16);
                 if (p.residual != nullptr) {
@@ -774,7 +779,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
             for (int i = 0; i < 8; ++i) {
               const int rr = i * 4 + (lane >> 3);
               const int grow = my_rowmap[rr];
-              if (grow >= 0 && col_ok && p.debug != 4) {
+              if (grow >= 0 && col_ok && dbgmode != 4) {
                 const int sw = ch ^ (rr & 7);
                 float4 val = *reinterpret_cast<const float4*>(my_stage + rr * 128 + sw * 16);
                 if (pre) {

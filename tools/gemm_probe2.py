@@ -1,4 +1,5 @@
-"""MMA-rate probe: plain GEMM M=86016, K=2880, N=3840 with a forced N tile (PN_GEMM_BN) in CTA-pair mode."""
+"""(PN_GEMM_DEBUG switches need a diagnostics build: PN_GEMM_ROLE_TIMERS=1 python -m panacea_b200.build --force)
+MMA-rate probe: plain GEMM M=86016, K=2880, N=3840 with a forced N tile (PN_GEMM_BN) in CTA-pair mode."""
 import os, sys
 from pathlib import Path
 import torch

@@ -1,5 +1,6 @@
 """Epilogue/mainloop decomposition of the K=320 transformer GEMMs at the L0 shape (PN_GEMM_DEBUG = 0..4), and the
-per-role cycle accounting of CTA 0 (PN_GEMM_DEBUG=5 on a library built with PN_GEMM_ROLE_TIMERS=1)."""
+per-role cycle accounting of CTA 0 (PN_GEMM_DEBUG=5). All PN_GEMM_DEBUG / PN_ATTN_DEBUG switches only exist in a
+diagnostics build: PN_GEMM_ROLE_TIMERS=1 python -m panacea_b200.build --force (the product build folds them away)."""
 import ctypes, os, sys
 from pathlib import Path
 import torch

@@ -1,4 +1,5 @@
-"""UMMA issue-rate probe: MMA-only GEMM (PN_GEMM_DEBUG=1) at several N tiles, 1-CTA (PN_GEMM_MODE=1) or CTA pairs (=2).
+"""(needs a diagnostics build: PN_GEMM_ROLE_TIMERS=1 python -m panacea_b200.build --force)
+UMMA issue-rate probe: MMA-only GEMM (PN_GEMM_DEBUG=1) at several N tiles, 1-CTA (PN_GEMM_MODE=1) or CTA pairs (=2).
 Prints cycles per tcgen05.mma (K=16) assuming the SM clock given by nvidia-smi at run time."""
 import ctypes, os, subprocess, sys
 from pathlib import Path
