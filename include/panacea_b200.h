@@ -29,9 +29,18 @@
 extern "C" {
 #endif
 
-#define PN_ABI_VERSION 1
+#define PN_ABI_VERSION 2
 
 enum pn_status { PN_STATUS_OK = 0, PN_STATUS_INVALID = -1, PN_STATUS_CUDA = -2, PN_STATUS_UNSUPPORTED = -3 };
+
+/* How a producer writes the A operand of the GEMM that follows it ("operand_mode" arguments below).
+ *  PN_OPERAND_BF16   bf16 [rows, C]                   — the fast path (bf16 products, fp32 accumulation);
+ *  PN_OPERAND_SPLIT3 bf16 [rows, 3C] = [hi | lo | hi] — parity mode: hi = bf16(v), lo = bf16(v - hi); against weights
+ *                    packed [W_hi | W_hi | W_lo] per tap the same pn_gemm kernel yields fp32-class products
+ *                    (hi W_hi + lo W_hi + hi W_lo), which is how the reference's fp32 math (wrappers.py:37-70 on CPU)
+ *                    is matched to rtol 1e-3 / atol 1e-4;
+ *  PN_OPERAND_F32    fp32 [rows, C]                   — input of a CUDA-core consumer in parity mode. */
+enum pn_operand_mode { PN_OPERAND_BF16 = 0, PN_OPERAND_SPLIT3 = 1, PN_OPERAND_F32 = 2 };
 
 const char* pn_last_error(void);
 int pn_abi_version(void);
@@ -103,6 +112,14 @@ int pn_attention_temporal(const void* q, const void* k, const void* v, void* out
                           int64_t pixels, int32_t heads, int32_t head_dim, int64_t ld, int64_t out_ld, float scale,
                           void* stream);
 
+/* Parity-mode attention: the same geometry (pn_attn_args; q/k/v are fp32 here, strides in floats, out_ld must be
+ * heads*head_dim), fp32 products / softmax / accumulation on CUDA cores, head_dim 64 or 80; `out` is written as the
+ * operand of the to_out GEMM in `operand_mode`. Same reference call sites as pn_attention / pn_attention_temporal. */
+int pn_attention_f32(const pn_attn_args* args, int operand_mode, void* stream);
+int pn_attention_temporal_f32(const float* q, const float* k, const float* v, void* out, int64_t batch, int64_t T,
+                              int64_t pixels, int32_t heads, int32_t head_dim, int64_t ld, float scale, int operand_mode,
+                              void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Normalisation (fp32 residual stream in, bf16 MMA operand out)
  * ---------------------------------------------------------------------------------------------- */
@@ -111,17 +128,17 @@ int pn_attention_temporal(const void* q, const void* k, const void* v, void* out
  * all six views of the panorama. raw_bf16 (optional) receives a plain bf16 cast of x (input of the 1x1 skip
  * convolution, openaimodel.py:486). workspace: pn_groupnorm_workspace_floats(...) floats. */
 int64_t pn_groupnorm_workspace_floats(int64_t frames, int64_t pixels, int64_t channels);
-int pn_groupnorm_silu(const float* x, const float* gamma, const float* beta, void* y_bf16, void* raw_bf16,
+int pn_groupnorm_silu(const float* x, const float* gamma, const float* beta, void* y, void* raw,
                       float* workspace, int64_t frames, int64_t pixels, int64_t channels, float eps, int act_silu,
-                      void* stream);
+                      int operand_mode, void* stream);
 /* GroupNorm(32, C) over (C/32, T) per pixel [+ SiLU] on x[batch, T, pixels, C]: the reference applies
  * nn.GroupNorm to the "(b h w) c t" rearrangement (openaimodel.py:509-512, 534-537). */
-int pn_groupnorm_pixel_silu(const float* x, const float* gamma, const float* beta, void* y_bf16, int64_t batch,
+int pn_groupnorm_pixel_silu(const float* x, const float* gamma, const float* beta, void* y, int64_t batch,
                             int64_t frames_per_seq, int64_t pixels, int64_t channels, float eps, int act_silu,
-                            void* stream);
+                            int operand_mode, void* stream);
 /* nn.LayerNorm(C) per token, eps 1e-5 (attention.py:699-701). */
-int pn_layernorm(const float* x, const float* gamma, const float* beta, void* y_bf16, int64_t rows, int64_t channels,
-                 float eps, void* stream);
+int pn_layernorm(const float* x, const float* gamma, const float* beta, void* y, int64_t rows, int64_t channels,
+                 float eps, int operand_mode, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Convolutions that cannot feed a 64-wide UMMA K block, layout and sampler helpers
@@ -131,25 +148,32 @@ int pn_layernorm(const float* x, const float* gamma, const float* beta, void* y_
 int pn_conv3x3_direct(const void* x, int x_is_bf16, const float* w_packed, const float* bias, const float* addend,
                       float* y_f32, void* y_bf16, int64_t frames, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
                       int64_t Cout_pad, int stride, int act_silu, void* stream);
-/* im2col for the stride-2 Downsample conv (openaimodel.py:187): fp32 [F,H,W,C] -> bf16 [F*Ho*Wo, 9*C]. */
-int pn_im2col3x3_s2(const float* x, void* out_bf16, int64_t frames, int64_t H, int64_t W, int64_t C, void* stream);
-/* F.interpolate(scale_factor=2, mode="nearest") of Upsample (openaimodel.py:133-140), fp32 -> bf16. */
-int pn_upsample2x_bf16(const float* x, void* y_bf16, int64_t frames, int64_t H, int64_t W, int64_t C, void* stream);
+/* im2col for the stride-2 Downsample conv (openaimodel.py:187): fp32 [F,H,W,C] -> operand [F*Ho*Wo, 9 taps x C]
+ * (each tap is one operand row of C channels: 9*C bf16, or 9*3C in split3 mode). */
+int pn_im2col3x3_s2(const float* x, void* out, int64_t frames, int64_t H, int64_t W, int64_t C, int operand_mode,
+                    void* stream);
+/* F.interpolate(scale_factor=2, mode="nearest") of Upsample (openaimodel.py:133-140), fp32 -> operand. */
+int pn_upsample2x(const float* x, void* y, int64_t frames, int64_t H, int64_t W, int64_t C, int operand_mode, void* stream);
 /* out = cat([h, skip + ctrl], channel) — decoder skip join (controlmodel.py:193-195); ctrl may be NULL. */
 int pn_concat_add(const float* h, const float* skip, const float* ctrl, float* out, int64_t rows, int64_t C1,
                   int64_t C2, void* stream);
 int pn_add_inplace(float* x, const float* y, int64_t n, void* stream);      /* h += control.pop() (controlmodel.py:192) */
-int pn_cast_bf16(const float* x, void* y_bf16, int64_t n, void* stream);
+/* fp32 [rows, C] -> operand (bf16 or split3). */
+int pn_cast_operand(const float* x, void* y, int64_t rows, int64_t C, int operand_mode, void* stream);
+/* Parity-mode GEGLU (attention.py:97-99, exact erf GELU) on the fp32 output of the ff.net.0 GEMM whose columns are in
+ * pn_gemm's GEGLU packing (blocks of 32 = 16 value + 16 gate columns): in fp32 [rows, 2*inner] -> operand [rows, inner]. */
+int pn_geglu_operand(const float* in, void* y, int64_t rows, int64_t inner, int operand_mode, void* stream);
 /* [batch, A, B] -> out[batch, B, ld] at column offset off: NCHW <-> channels-last at the module boundary
  * (also performs the channel concat of wrappers.py:41). */
 int pn_transpose_f32(const float* in, float* out, int64_t batch, int64_t A, int64_t B, int64_t out_ld, int64_t out_off,
                      void* stream);
-/* util.py:224-248 timestep_embedding (cos | sin halves). */
-int pn_timestep_embedding(const int64_t* t, float* out, int64_t n, int64_t dim, void* stream);
+/* util.py:224-248 timestep_embedding (cos | sin halves). freqs: optional fp32 [dim/2] frequency table computed by the
+ * host with the reference's expression (bit-identical arguments t*f); NULL = computed in the kernel. */
+int pn_timestep_embedding(const int64_t* t, float* out, int64_t n, int64_t dim, const float* freqs, void* stream);
 /* y = act_out(W act_in(x) + b) for M <= 32 rows: time_embed MLP and per-block emb_layers
  * (openaimodel.py:936-943, 439-445). */
-int pn_linear_small(const float* x, const void* W_bf16, const float* bias, float* y, int64_t M, int64_t N, int64_t K,
-                    int64_t ldy, int silu_in, int silu_out, void* stream);
+int pn_linear_small(const float* x, const void* W, int w_is_f32, const float* bias, float* y, int64_t M, int64_t N,
+                    int64_t K, int64_t ldy, int silu_in, int silu_out, void* stream);
 /* One Euler step with classifier-free guidance, reference operation order (denoiser.py:22-28, guiders.py:25-29,
  * sampling_utils.py:7-9,39-40, sampling.py:103-110). net2 = [uncond ; cond] halves of n elements each: the network's
  * eps prediction (net_is_denoised = 0; the denoiser's c_out = -sigma_q, c_skip = 1 are applied here, sigma_q being
@@ -157,6 +181,10 @@ int pn_linear_small(const float* x, const void* W_bf16, const float* bias, float
  * x is updated in place; x_in_next (optional, 2n elements) receives x_new * c_in_next duplicated. */
 int pn_cfg_euler_step(float* x, const float* net2, float* x_in_next, int64_t n, float sigma, float sigma_q,
                       float sigma_next, float cfg_scale, float c_in_next, int net_is_denoised, void* stream);
+/* Content fingerprint of a device buffer (two order-independent 64-bit sums over its 32-bit words) -> out2[2] on the
+ * device. The wrapper keys its step-invariant conditioning cache (BEV hint stem, text K/V; wrappers.py:37-70 recomputes
+ * them every step) on the CONTENT of c["cond_feat"] / c["crossattn"]: addresses are recycled by the allocator. */
+int pn_fingerprint(const void* x, int64_t nbytes, uint64_t* out2, void* stream);
 /* out[c*n + i] = x[i] * s for c < copies (prepare_sampling_loop x *= sqrt(1+sigma0^2), CFG batch doubling). */
 int pn_scale_dup(const float* x, float* out, int64_t n, float s, int copies, void* stream);
 

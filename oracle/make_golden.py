@@ -57,8 +57,13 @@ def golden_kat() -> dict:
 
 
 @torch.no_grad()
-def golden_sampler(case: Cs.EpsCase, num_steps: int = 10, scale: float = 5.0) -> dict:
-    """Full reference loop: EulerEDMSampler + VanillaCFG + DiscreteDenoiser around the reference wrapper."""
+def golden_sampler(case: Cs.EpsCase, num_steps: int = 10, scale: float = 5.0, use_last_frame: bool = False,
+                   share_noise_level: float = 0.07, trajectory: bool = False) -> dict:
+    """Full reference loop: EulerEDMSampler + VanillaCFG + DiscreteDenoiser around the reference wrapper.
+    use_last_frame: BASELINE config 4 — the concat latent is zero except for the last frame
+    (nuscenes_datasets_video.py:559-566) and the initial noise is mixed as DiffusionEngine3D.sample does
+    (diffusion.py:242-249, restated below because the Lightning module itself needs the conditioner/VAE configs).
+    trajectory: also record x at the start of every step (error-vs-step curves on the GPU)."""
     ref = R.import_reference()
     model = R.build_reference_model(case.unet_kwargs())
     model.load_state_dict(Cs.make_weights(case), strict=True)
@@ -71,24 +76,35 @@ def golden_sampler(case: Cs.EpsCase, num_steps: int = 10, scale: float = 5.0) ->
         num_steps=num_steps, device="cpu",
         discretization_config={"target": "sgm.modules.diffusionmodules.discretizer.LegacyDDPMDiscretization"},
         guider_config={"target": "sgm.modules.diffusionmodules.guiders.VanillaCFG", "params": {"scale": scale}})
-    x, c, uc = sampler_inputs(case)
-    calls = []
+    x, c, uc = sampler_inputs(case, use_last_frame)
+    calls, traj = [], []
+    if use_last_frame and share_noise_level > 0.0:
+        # diffusion.py:244-249: randn = randn + repeat(concat[-1], "c h w -> t c h w") * share_noise_level
+        x = x + c["concat"][-1].unsqueeze(0).expand_as(x) * share_noise_level
 
     def denoise(xx, sigma, cc):
         calls.append(int(den.sigma_to_idx(sigma)[0]))
+        if trajectory:
+            traj.append(xx[: xx.shape[0] // 2].clone())
         return den(model, xx, sigma, cc)
 
     with R.view_height_shim(case.H, case.w):
         out = sampler(denoise, x.clone(), c, uc)
-    return {"meta": case.meta(), "num_steps": num_steps, "scale": scale, "x_final": out, "timestep_indices": calls}
+    res = {"meta": case.meta(), "num_steps": num_steps, "scale": scale, "x_final": out, "timestep_indices": calls,
+           "use_last_frame": use_last_frame, "share_noise_level": share_noise_level}
+    if trajectory:
+        res["x_steps"] = torch.stack(traj)        # x as the guider sees it at the start of step i (already * sqrt(1+s0^2))
+    return res
 
 
-def sampler_inputs(case: Cs.EpsCase):
+def sampler_inputs(case: Cs.EpsCase, use_last_frame: bool = False):
     """One sequence (case.b is ignored: the sampler doubles the batch itself): init noise, c and uc dicts."""
     g = torch.Generator(device="cpu").manual_seed(case.input_seed + 100)
     T, W = case.num_frames, 6 * case.w
     x = torch.randn(T, 4, case.H, W, generator=g)
     concat = torch.randn(T, 4, case.H, W, generator=g)
+    if use_last_frame:
+        concat[:-1].zero_()
     hint = torch.rand(T, 19, 8 * case.H, 8 * W, generator=g)
     c = {"concat": concat, "cond_feat": hint, "crossattn": torch.randn(1, 77, case.context_dim, generator=g)}
     uc = {"concat": concat, "cond_feat": hint, "crossattn": torch.randn(1, 77, case.context_dim, generator=g)}
@@ -118,6 +134,16 @@ def main(argv=None):
         g = golden_sampler(case)
         torch.save(g, GOLDEN / f"sampler_{case.name}.pt")
         print(f"sampler_{case.name}.pt rms={g['x_final'].pow(2).mean().sqrt():.4f} idx={g['timestep_indices']}")
+    # 25-step (the YAML's count, with use_last_frame share-noise init = BASELINE config 4) and 50-step (BASELINE
+    # config 2) reference loops on the GPU-runnable head_dim-64 model, with the per-step trajectory
+    for steps, ulf in ((25, True), (50, False)):
+        name = f"sampler_{Cs.SAMPLER_CASE.name}_{steps}"
+        if only and name not in only and "sampler_loops" not in only:
+            continue
+        t0 = time.time()
+        g = golden_sampler(Cs.SAMPLER_CASE, num_steps=steps, use_last_frame=ulf, trajectory=True)
+        torch.save(g, GOLDEN / f"{name}.pt")
+        print(f"{name}.pt rms={g['x_final'].pow(2).mean().sqrt():.4f} {time.time() - t0:.1f}s")
 
 
 if __name__ == "__main__":

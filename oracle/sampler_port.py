@@ -69,14 +69,14 @@ def cfg_prepare(x, s, c: dict, uc: dict):
 
 
 @torch.no_grad()
-def euler_edm_sample(network, x, cond: dict, uc: dict, num_steps: int, scale: float = 5.0, denoiser=None):
+def euler_edm_sample(network, x, cond: dict, uc: dict, num_steps: int, scale: float = 5.0, denoiser=None, max_steps=None):
     """sampling.py:44-60,96-133,214-218 with s_churn=0 (gamma=0): deterministic Euler steps in sigma space.
     `network(x_in, idx, cond_dict) -> eps`."""
     den = DiscreteDenoiserPort() if denoiser is None else denoiser
     sigmas = legacy_ddpm_sigmas(num_steps)
     x = x * torch.sqrt(1.0 + sigmas[0] ** 2.0)
     s_in = x.new_ones([x.shape[0]])
-    for i in range(len(sigmas) - 1):
+    for i in range(len(sigmas) - 1 if max_steps is None else min(max_steps, len(sigmas) - 1)):
         sigma, nxt = s_in * sigmas[i], s_in * sigmas[i + 1]
         xx, ss, cc = cfg_prepare(x, sigma, cond, uc)
         d2 = den(network, xx, ss, cc)

@@ -53,22 +53,26 @@ SIGNATURES: dict[str, tuple] = {
     "pn_gemm": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
     "pn_attention": (C.c_int, [C.POINTER(AttnArgs), _vp]),
     "pn_attention_temporal": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _i64, _i64, _f32, _vp]),
+    "pn_attention_f32": (C.c_int, [C.POINTER(AttnArgs), C.c_int, _vp]),
+    "pn_attention_temporal_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _i64, _f32, C.c_int, _vp]),
     "pn_groupnorm_workspace_floats": (_i64, [_i64, _i64, _i64]),
-    "pn_groupnorm_silu": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _f32, C.c_int, _vp]),
-    "pn_groupnorm_pixel_silu": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _f32, C.c_int, _vp]),
-    "pn_layernorm": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _f32, _vp]),
+    "pn_groupnorm_silu": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _f32, C.c_int, C.c_int, _vp]),
+    "pn_groupnorm_pixel_silu": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _f32, C.c_int, C.c_int, _vp]),
+    "pn_layernorm": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _f32, C.c_int, _vp]),
     "pn_conv3x3_direct": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64,
                                     C.c_int, C.c_int, _vp]),
-    "pn_im2col3x3_s2": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp]),
-    "pn_upsample2x_bf16": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp]),
+    "pn_im2col3x3_s2": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, C.c_int, _vp]),
+    "pn_upsample2x": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, C.c_int, _vp]),
     "pn_concat_add": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "pn_add_inplace": (C.c_int, [_vp, _vp, _i64, _vp]),
-    "pn_cast_bf16": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "pn_cast_operand": (C.c_int, [_vp, _vp, _i64, _i64, C.c_int, _vp]),
+    "pn_geglu_operand": (C.c_int, [_vp, _vp, _i64, _i64, C.c_int, _vp]),
     "pn_transpose_f32": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp]),
-    "pn_timestep_embedding": (C.c_int, [_vp, _vp, _i64, _i64, _vp]),
-    "pn_linear_small": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, C.c_int, C.c_int, _vp]),
+    "pn_timestep_embedding": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
+    "pn_linear_small": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _i64, _i64, _i64, _i64, C.c_int, C.c_int, _vp]),
     "pn_cfg_euler_step": (C.c_int, [_vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, C.c_int, _vp]),
     "pn_scale_dup": (C.c_int, [_vp, _vp, _i64, _f32, C.c_int, _vp]),
+    "pn_fingerprint": (C.c_int, [_vp, _i64, _vp, _vp]),
 }
 
 

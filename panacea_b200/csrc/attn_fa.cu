@@ -490,12 +490,6 @@ extern "C" int pn_attention(const pn_attn_args* a, void* stream_v) {
     rc = cached_tmap_bf16(&p.mapV, a->v, 5, dims, str, box, 128);
     if (rc != PN_OK) return rc;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    for (int i = 0; i < 10; ++i)
-      PN_CHECK_CUDA(cudaFuncSetAttribute(fa_kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_TOTAL));
-    attr_set = true;
-  }
   p.tiles_per_group = p.tiles_x * p.tiles_y;
   p.pairs = (p.tiles_per_group + 1) / 2;
   const long long items = (long long)p.pairs * a->heads * a->V * a->F;
@@ -504,7 +498,12 @@ extern "C" int pn_attention(const pn_attn_args* a, void* stream_v) {
   const int grid = items < sm_count() ? (int)items : sm_count();
   const int nch = p.kv_n / 16;
   const int slot = nch == 8 ? 4 : nch == 7 ? 3 : nch == 5 ? 2 : nch == 2 ? 1 : 0;
-  fa_kernels[(p.kv_rows < p.kv_n ? 5 : 0) + slot]<<<grid, FA_THREADS, FA_SMEM_TOTAL, reinterpret_cast<cudaStream_t>(stream_v)>>>(p);
+  const FaKernel kern = fa_kernels[(p.kv_rows < p.kv_n ? 5 : 0) + slot];
+  {
+    const int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), FA_SMEM_TOTAL);
+    if (rc != PN_OK) return rc;
+  }
+  kern<<<grid, FA_THREADS, FA_SMEM_TOTAL, reinterpret_cast<cudaStream_t>(stream_v)>>>(p);
   PN_CHECK_CUDA(cudaGetLastError());
   return PN_OK;
 }

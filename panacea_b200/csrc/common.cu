@@ -156,15 +156,35 @@ int cached_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
   return PN_OK;
 }
 
+// Per-device caches: the SM count and the opt-in dynamic shared-memory limit of a kernel are properties of the
+// CURRENT device / context, so both are keyed by the device ordinal (a process may drive several GPUs).
+static std::mutex g_dev_mu;
+static int g_sm_count[64];
+static std::unordered_map<unsigned long long, size_t> g_smem_attr;   // (func address ^ device << 56) -> bytes set
+
 int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  if (g_sm_count[dev] == 0) {
+    int n = 0;
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+    g_sm_count[dev] = n > 0 ? n : 148;
   }
-  return n;
+  return g_sm_count[dev];
+}
+
+int ensure_dyn_smem(const void* func, size_t bytes) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long key = (unsigned long long)reinterpret_cast<uintptr_t>(func) ^ ((unsigned long long)(dev & 0xff) << 56);
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  auto it = g_smem_attr.find(key);
+  if (it != g_smem_attr.end() && it->second >= bytes) return PN_OK;
+  PN_CHECK_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  g_smem_attr[key] = bytes;
+  return PN_OK;
 }
 
 }  // namespace pn

@@ -40,6 +40,8 @@ int cached_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64
 int cached_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_elems, const uint32_t* box, int swizzle_bytes);
 
-int sm_count();
+int sm_count();                                          // of the current device
+// opt in to `bytes` of dynamic shared memory for `func` on the current device (once per device and size)
+int ensure_dyn_smem(const void* func, size_t bytes);
 
 }  // namespace pn

@@ -3,6 +3,7 @@
 // fused classifier-free-guidance + Euler update of the sampler.
 #include "common.cuh"
 #include "ptx.cuh"
+#include "operand.cuh"
 #include "../../include/panacea_b200.h"
 
 namespace pn {
@@ -26,9 +27,9 @@ __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict
   }
 }
 
-// ---------------------------------------------------------------- nearest 2x upsample, fp32 -> bf16
-__global__ void upsample2x_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int F, int H, int W,
-                                  int C) {
+// ---------------------------------------------------------------- nearest 2x upsample, fp32 -> GEMM operand
+template <int OP>
+__global__ void upsample2x_kernel(const float* __restrict__ x, void* __restrict__ y, int F, int H, int W, int C) {
   const int c8n = C / 8;
   const size_t total = (size_t)F * (2 * H) * (2 * W) * c8n;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
@@ -40,8 +41,8 @@ __global__ void upsample2x_kernel(const float* __restrict__ x, __nv_bfloat16* __
     const float* src = x + (((size_t)f * H + (oy >> 1)) * W + (ox >> 1)) * C + c8 * 8;
     const float4 a = *reinterpret_cast<const float4*>(src);
     const float4 b = *reinterpret_cast<const float4*>(src + 4);
-    *reinterpret_cast<uint4*>(y + (((size_t)f * 2 * H + oy) * 2 * W + ox) * C + c8 * 8) =
-        make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    store_op8<OP>(y, ((size_t)f * 2 * H + oy) * 2 * W + ox, C, c8 * 8, v);
   }
 }
 
@@ -78,21 +79,50 @@ __global__ void add_inplace_kernel(float* __restrict__ x, const float* __restric
   }
 }
 
-__global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t n4) {
+// fp32 [rows, C] -> GEMM operand [rows, C] (bf16) or [rows, 3C] (split3)
+template <int OP>
+__global__ void cast_operand_kernel(const float* __restrict__ x, void* __restrict__ y, size_t rows, int C) {
+  const int c4n = C / 4;
+  const size_t n4 = rows * (size_t)c4n;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (size_t)gridDim.x * blockDim.x) {
     const float4 a = reinterpret_cast<const float4*>(x)[e];
-    reinterpret_cast<uint2*>(y)[e] = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+    const float v[4] = {a.x, a.y, a.z, a.w};
+    store_op4<OP>(y, e / c4n, C, (int)(e % c4n) * 4, v);
+  }
+}
+
+// GEGLU on an fp32 GEMM output whose columns are packed in blocks of 32 (16 value columns, then the 16 gate columns
+// of the same outputs — the layout of pn_gemm's fused GEGLU epilogue): out[row, 16 b + i] = in[row, 32 b + i] *
+// gelu_erf(in[row, 32 b + 16 + i]) with the exact erf GELU of the reference (attention.py:97-99). Parity mode only.
+template <int OP>
+__global__ void geglu_operand_kernel(const float* __restrict__ in, void* __restrict__ y, size_t rows, int inner) {
+  const int c4n = inner / 4;
+  const size_t n4 = rows * (size_t)c4n;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = e / c4n;
+    const int col = (int)(e % c4n) * 4;
+    const float* src = in + row * (size_t)(2 * inner) + (col / 16) * 32 + (col % 16);
+    const float4 val = *reinterpret_cast<const float4*>(src);
+    const float4 gate = *reinterpret_cast<const float4*>(src + 16);
+    const float vv[4] = {val.x, val.y, val.z, val.w}, gg[4] = {gate.x, gate.y, gate.z, gate.w};
+    float o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = vv[i] * (0.5f * gg[i] * (1.0f + erff(gg[i] * 0.70710678118654752f)));
+    store_op4<OP>(y, row, inner, col, o);
   }
 }
 
 // ---------------------------------------------------------------- sinusoidal timestep embedding
 // util.py:224-248: emb[n] = [cos(t f_k), sin(t f_k)], f_k = exp(-ln(10000) k / half)
-__global__ void timestep_embedding_kernel(const long long* __restrict__ t, float* __restrict__ out, int n, int dim) {
+// freqs (optional): the caller's fp32 table of the dim/2 frequencies (the host computes it with the reference's own
+// expression, so the arguments t * f_k are bit-identical to the reference's — t is up to 999, an ulp of f_k matters).
+__global__ void timestep_embedding_kernel(const long long* __restrict__ t, float* __restrict__ out, int n, int dim,
+                                          const float* __restrict__ freqs) {
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * half) return;
   const int row = i / half, k = i - row * half;
-  const float freq = expf(-9.210340371976184f * (float)k / (float)half);
+  const float freq = freqs ? freqs[k] : expf(-9.210340371976184f * (float)k / (float)half);
   const float arg = (float)t[row] * freq;
   out[(size_t)row * dim + k] = cosf(arg);
   out[(size_t)row * dim + half + k] = sinf(arg);
@@ -102,8 +132,17 @@ __global__ void timestep_embedding_kernel(const long long* __restrict__ t, float
 // ---------------------------------------------------------------- small-M linear (time-embedding MLPs)
 // y[m, n] = act_out( b[n] + sum_k W[n,k] * act_in(x[m,k]) ), fp32 activations, bf16 weights, M <= 32.
 // One warp computes 4 output columns for all rows (weights are the traffic; x stays in L1/L2).
-template <int MAXM>
-__global__ void __launch_bounds__(128) linear_small_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ W,
+template <typename TW>
+__device__ __forceinline__ float2 load_w2(const TW* p);
+template <>
+__device__ __forceinline__ float2 load_w2<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+}
+template <>
+__device__ __forceinline__ float2 load_w2<float>(const float* p) { return *reinterpret_cast<const float2*>(p); }
+
+template <int MAXM, typename TW>
+__global__ void __launch_bounds__(128) linear_small_kernel(const float* __restrict__ x, const TW* __restrict__ W,
                                                            const float* __restrict__ bias, float* __restrict__ y, int M,
                                                            int N, int K, long long ldy, int silu_in, int silu_out) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -120,7 +159,7 @@ __global__ void __launch_bounds__(128) linear_small_kernel(const float* __restri
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = min(n0 + j, N - 1);
-      w[j] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(W + (size_t)n * K + k));
+      w[j] = load_w2<TW>(W + (size_t)n * K + k);
     }
 #pragma unroll
     for (int m = 0; m < MAXM; ++m) {
@@ -148,8 +187,10 @@ __global__ void __launch_bounds__(128) linear_small_kernel(const float* __restri
   }
 }
 
-// ---------------------------------------------------------------- stride-2 3x3 im2col, fp32 NHWC -> bf16 [rows, 9C]
-__global__ void im2col_s2_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int F, int H, int W, int C,
+// ---------------------------------------------------------------- stride-2 3x3 im2col, fp32 NHWC -> operand [rows*9, C]
+// (viewed by the GEMM as [rows, 9*C] or [rows, 9*3C]: every tap is one operand row)
+template <int OP>
+__global__ void im2col_s2_kernel(const float* __restrict__ x, void* __restrict__ out, int F, int H, int W, int C,
                                  int Ho, int Wo) {
   const int c8n = C / 8;
   const size_t total = (size_t)F * Ho * Wo * 9 * c8n;
@@ -161,14 +202,14 @@ __global__ void im2col_s2_kernel(const float* __restrict__ x, __nv_bfloat16* __r
     const int oy = (int)(r % Ho);
     const int f = (int)(r / Ho);
     const int iy = oy * 2 - 1 + tap / 3, ix = ox * 2 - 1 + tap % 3;
-    uint4 v = make_uint4(0, 0, 0, 0);
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
       const float* src = x + (((size_t)f * H + iy) * W + ix) * C + c8 * 8;
       const float4 a = *reinterpret_cast<const float4*>(src);
       const float4 b = *reinterpret_cast<const float4*>(src + 4);
-      v = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
     }
-    *reinterpret_cast<uint4*>(out + ((((size_t)f * Ho + oy) * Wo + ox) * 9 + tap) * C + c8 * 8) = v;
+    store_op8<OP>(out, (((size_t)f * Ho + oy) * Wo + ox) * 9 + tap, C, c8 * 8, v);
   }
 }
 
@@ -204,6 +245,28 @@ __global__ void scale_dup_kernel(const float* __restrict__ x, float* __restrict_
   }
 }
 
+// ---------------------------------------------------------------- content fingerprint of a device buffer
+// Two order-independent 64-bit sums over the 32-bit words (plain sum, position-weighted sum). The conditioning cache of
+// the wrapper keys on CONTENT with it: tensor addresses are recycled by the allocator and the reference's guider
+// rebuilds its torch.cat-ed dict every step, so neither identity nor address says whether the BEV hint / text changed.
+__global__ void fingerprint_kernel(const uint32_t* __restrict__ x, size_t nwords, unsigned long long* __restrict__ out2) {
+  unsigned long long s1 = 0ull, s2 = 0ull;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x) {
+    const unsigned long long w = x[i];
+    s1 += w;
+    s2 += w * ((unsigned long long)i * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&out2[0], s1);
+    atomicAdd(&out2[1], s2);
+  }
+}
+
 static inline int grid_for(size_t total, int threads = 256) {
   size_t g = (total + threads - 1) / threads;
   const size_t cap = (size_t)16 * sm_count();
@@ -227,12 +290,13 @@ extern "C" int pn_transpose_f32(const float* in, float* out, int64_t batch, int6
   return PN_OK;
 }
 
-extern "C" int pn_upsample2x_bf16(const float* x, void* y_bf16, int64_t frames, int64_t H, int64_t W, int64_t C,
-                                  void* stream_v) {
-  PN_REQUIRE(x && y_bf16 && frames > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "pn_upsample2x_bf16: bad arguments");
+extern "C" int pn_upsample2x(const float* x, void* y, int64_t frames, int64_t H, int64_t W, int64_t C, int operand_mode,
+                             void* stream_v) {
+  PN_REQUIRE(x && y && frames > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "pn_upsample2x: bad arguments");
+  PN_REQUIRE(operand_mode >= 0 && operand_mode <= 2, "pn_upsample2x: operand_mode %d", operand_mode);
   const size_t total = (size_t)frames * 4 * H * W * (C / 8);
-  upsample2x_kernel<<<grid_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(
-      x, reinterpret_cast<__nv_bfloat16*>(y_bf16), (int)frames, (int)H, (int)W, (int)C);
+  PN_DISPATCH_OP(operand_mode, (upsample2x_kernel<OP><<<grid_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(
+      x, y, (int)frames, (int)H, (int)W, (int)C)));
   PN_CHECK_CUDA(cudaGetLastError());
   return PN_OK;
 }
@@ -254,46 +318,66 @@ extern "C" int pn_add_inplace(float* x, const float* y, int64_t n, void* stream_
   return PN_OK;
 }
 
-extern "C" int pn_cast_bf16(const float* x, void* y_bf16, int64_t n, void* stream_v) {
-  PN_REQUIRE(x && y_bf16 && n > 0 && n % 4 == 0, "pn_cast_bf16: bad arguments");
-  cast_bf16_kernel<<<grid_for((size_t)n / 4), 256, 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(
-      x, reinterpret_cast<__nv_bfloat16*>(y_bf16), (size_t)n / 4);
+extern "C" int pn_cast_operand(const float* x, void* y, int64_t rows, int64_t C, int operand_mode, void* stream_v) {
+  PN_REQUIRE(x && y && rows > 0 && C > 0 && C % 4 == 0, "pn_cast_operand: bad arguments");
+  PN_REQUIRE(operand_mode == PN_OP_BF16 || operand_mode == PN_OP_SPLIT3, "pn_cast_operand: operand_mode %d", operand_mode);
+  const size_t n4 = (size_t)rows * (size_t)(C / 4);
+  PN_DISPATCH_OP(operand_mode, (cast_operand_kernel<OP><<<grid_for(n4), 256, 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(
+      x, y, (size_t)rows, (int)C)));
   PN_CHECK_CUDA(cudaGetLastError());
   return PN_OK;
 }
 
-extern "C" int pn_timestep_embedding(const int64_t* t, float* out, int64_t n, int64_t dim, void* stream_v) {
+extern "C" int pn_geglu_operand(const float* in, void* y, int64_t rows, int64_t inner, int operand_mode, void* stream_v) {
+  PN_REQUIRE(in && y && rows > 0 && inner > 0 && inner % 16 == 0, "pn_geglu_operand: bad arguments");
+  PN_REQUIRE(operand_mode >= 0 && operand_mode <= 2, "pn_geglu_operand: operand_mode %d", operand_mode);
+  const size_t n4 = (size_t)rows * (size_t)(inner / 4);
+  PN_DISPATCH_OP(operand_mode, (geglu_operand_kernel<OP><<<grid_for(n4), 256, 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(
+      in, y, (size_t)rows, (int)inner)));
+  PN_CHECK_CUDA(cudaGetLastError());
+  return PN_OK;
+}
+
+extern "C" int pn_timestep_embedding(const int64_t* t, float* out, int64_t n, int64_t dim, const float* freqs,
+                                     void* stream_v) {
   PN_REQUIRE(t && out && n > 0 && dim >= 2, "pn_timestep_embedding: bad arguments");
   const int total = (int)(n * (dim / 2));
   timestep_embedding_kernel<<<(total + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(
-      reinterpret_cast<const long long*>(t), out, (int)n, (int)dim);
+      reinterpret_cast<const long long*>(t), out, (int)n, (int)dim, freqs);
   PN_CHECK_CUDA(cudaGetLastError());
   return PN_OK;
 }
 
-extern "C" int pn_linear_small(const float* x, const void* W_bf16, const float* bias, float* y, int64_t M, int64_t N,
-                               int64_t K, int64_t ldy, int silu_in, int silu_out, void* stream_v) {
-  PN_REQUIRE(x && W_bf16 && y, "pn_linear_small: null pointer");
+extern "C" int pn_linear_small(const float* x, const void* W_any, int w_is_f32, const float* bias, float* y, int64_t M,
+                               int64_t N, int64_t K, int64_t ldy, int silu_in, int silu_out, void* stream_v) {
+  PN_REQUIRE(x && W_any && y, "pn_linear_small: null pointer");
   PN_REQUIRE(M > 0 && M <= 32 && N > 0 && K > 0 && K % 2 == 0 && ldy >= N, "pn_linear_small: M=%lld N=%lld K=%lld unsupported",
              (long long)M, (long long)N, (long long)K);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
   const int warps = (int)((N + 3) / 4);
   const int blocks = (warps * 32 + 127) / 128;
-  const __nv_bfloat16* W = reinterpret_cast<const __nv_bfloat16*>(W_bf16);
-  if (M <= 8) linear_small_kernel<8><<<blocks, 128, 0, st>>>(x, W, bias, y, (int)M, (int)N, (int)K, ldy, silu_in, silu_out);
-  else if (M <= 16) linear_small_kernel<16><<<blocks, 128, 0, st>>>(x, W, bias, y, (int)M, (int)N, (int)K, ldy, silu_in, silu_out);
-  else linear_small_kernel<32><<<blocks, 128, 0, st>>>(x, W, bias, y, (int)M, (int)N, (int)K, ldy, silu_in, silu_out);
+#define PN_LS(TW)                                                                                                               \
+  do {                                                                                                                          \
+    const TW* W = reinterpret_cast<const TW*>(W_any);                                                                          \
+    if (M <= 8) linear_small_kernel<8, TW><<<blocks, 128, 0, st>>>(x, W, bias, y, (int)M, (int)N, (int)K, ldy, silu_in, silu_out);        \
+    else if (M <= 16) linear_small_kernel<16, TW><<<blocks, 128, 0, st>>>(x, W, bias, y, (int)M, (int)N, (int)K, ldy, silu_in, silu_out); \
+    else linear_small_kernel<32, TW><<<blocks, 128, 0, st>>>(x, W, bias, y, (int)M, (int)N, (int)K, ldy, silu_in, silu_out);              \
+  } while (0)
+  if (w_is_f32) PN_LS(float);
+  else PN_LS(__nv_bfloat16);
+#undef PN_LS
   PN_CHECK_CUDA(cudaGetLastError());
   return PN_OK;
 }
 
-extern "C" int pn_im2col3x3_s2(const float* x, void* out_bf16, int64_t frames, int64_t H, int64_t W, int64_t C,
+extern "C" int pn_im2col3x3_s2(const float* x, void* out, int64_t frames, int64_t H, int64_t W, int64_t C, int operand_mode,
                                void* stream_v) {
-  PN_REQUIRE(x && out_bf16 && frames > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "pn_im2col3x3_s2: bad arguments");
+  PN_REQUIRE(x && out && frames > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "pn_im2col3x3_s2: bad arguments");
+  PN_REQUIRE(operand_mode == PN_OP_BF16 || operand_mode == PN_OP_SPLIT3, "pn_im2col3x3_s2: operand_mode %d", operand_mode);
   const int Ho = (int)((H + 2 - 3) / 2 + 1), Wo = (int)((W + 2 - 3) / 2 + 1);
   const size_t total = (size_t)frames * Ho * Wo * 9 * (C / 8);
-  im2col_s2_kernel<<<grid_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(
-      x, reinterpret_cast<__nv_bfloat16*>(out_bf16), (int)frames, (int)H, (int)W, (int)C, Ho, Wo);
+  PN_DISPATCH_OP(operand_mode, (im2col_s2_kernel<OP><<<grid_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(
+      x, out, (int)frames, (int)H, (int)W, (int)C, Ho, Wo)));
   PN_CHECK_CUDA(cudaGetLastError());
   return PN_OK;
 }
@@ -311,6 +395,18 @@ extern "C" int pn_cfg_euler_step(float* x, const float* net2, float* x_in_next, 
 extern "C" int pn_scale_dup(const float* x, float* out, int64_t n, float s, int copies, void* stream_v) {
   PN_REQUIRE(x && out && n > 0 && copies >= 1, "pn_scale_dup: bad arguments");
   scale_dup_kernel<<<grid_for((size_t)n), 256, 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(x, out, (size_t)n, s, copies);
+  PN_CHECK_CUDA(cudaGetLastError());
+  return PN_OK;
+}
+
+extern "C" int pn_fingerprint(const void* x, int64_t nbytes, uint64_t* out2, void* stream_v) {
+  PN_REQUIRE(x && out2 && nbytes > 0 && nbytes % 4 == 0, "pn_fingerprint: bad arguments");
+  PN_REQUIRE((reinterpret_cast<uintptr_t>(x) & 3) == 0, "pn_fingerprint: pointer must be 4-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
+  PN_CHECK_CUDA(cudaMemsetAsync(out2, 0, 16, st));
+  const size_t nwords = (size_t)nbytes / 4;
+  fingerprint_kernel<<<grid_for(nwords), 256, 0, st>>>(reinterpret_cast<const uint32_t*>(x), nwords,
+                                                      reinterpret_cast<unsigned long long*>(out2));
   PN_CHECK_CUDA(cudaGetLastError());
   return PN_OK;
 }

@@ -886,10 +886,9 @@ template <int BN, int STAGES, int NCTA, int MODE>
 static int launch_gemm_mode(const GemmParams& p, cudaStream_t stream) {
   using S = GemmSmem<BN, STAGES, NCTA, MODE>;
   static_assert(S::TOTAL <= 232448, "shared memory budget exceeded");
-  static bool attr_set = false;
-  if (!attr_set) {
-    PN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, NCTA, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    attr_set = true;
+  {
+    const int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&gemm_tc_kernel<BN, STAGES, NCTA, MODE>), S::TOTAL);
+    if (rc != PN_OK) return rc;
   }
   const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
   const int num_tiles = ((tiles_m + NCTA - 1) / NCTA) * p.tiles_col;

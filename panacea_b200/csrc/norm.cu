@@ -8,8 +8,10 @@
 //    534-539: GroupNorm applied to the [(b h w), C, T] rearrangement) — here computed in place on the
 //    [b, T, P, C] layout, no rearrange copies;
 //  * LayerNorm(C) per token (attention.py:699-701, eps 1e-5).
+#include <cstdlib>
 #include "common.cuh"
 #include "ptx.cuh"
+#include "operand.cuh"
 #include "../../include/panacea_b200.h"
 
 namespace pn {
@@ -18,10 +20,6 @@ constexpr int GN_GROUPS = 32;
 constexpr int GN_THREADS = 512;
 constexpr int GN_MAX_FRAMES = 1024;
 constexpr size_t GN_WAVE_BYTES = 56ull << 20;   // frames processed together: their fp32 input stays resident in L2
-
-// arrival / departure counters of the per-frame CTA groups; zero at module load and reset by the last CTA to leave
-__device__ unsigned int g_gn_arrive[GN_MAX_FRAMES];
-__device__ unsigned int g_gn_depart[GN_MAX_FRAMES];
 
 // ---------------------------------------------------------------- spatial GN (+SiLU) -> bf16, ONE launch
 // The statistics of a frame need every pixel of it before the first output can be written, so the input is read
@@ -32,11 +30,18 @@ __device__ unsigned int g_gn_depart[GN_MAX_FRAMES];
 //   3. combines all partials of the frame in double precision (every CTA does the same sum in the same order),
 //   4. normalises ITS OWN pixel range again (L2 hits) -> y = act(x * rstd * gamma + beta - mean * rstd * gamma).
 // Thread layout in both passes: (pixel lane, 8-channel column), so scale/shift live in registers in pass 4.
-// partial: [frames][cpf][32 groups][2] floats.
+// partial: [frames][cpf][32 groups][2] floats; arrive: [frames] counters, both in the PER-CALL workspace (the counters
+// are zeroed by a memset node in front of the launch), so concurrent launches on other streams, other devices or an
+// aborted earlier launch cannot disturb the barrier.
+// PHASE 0: fused, launched COOPERATIVELY (the runtime guarantees the co-residency the barrier needs or refuses the
+// launch); PHASE 1 / 2: the same work as two ordinary launches (statistics, then normalise) for devices/contexts that
+// cannot hold the whole grid (MPS active-thread percentage, green contexts, SM partitioning).
+// OP: how the operand is stored (operand.cuh): bf16, split3 (parity mode) or fp32.
+template <int OP, int PHASE>
 __global__ void __launch_bounds__(GN_THREADS, 1)
 gn_fused_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ raw, float* __restrict__ partial, int P, int C,
-                int F, int wave, int cpf, float eps, int act_silu) {
+                void* __restrict__ y, void* __restrict__ raw, float* __restrict__ partial, unsigned int* __restrict__ arrive,
+                int P, int C, int F, int wave, int cpf, float eps, int act_silu) {
   extern __shared__ float gn_smem[];
   const int c8n = C / 8;
   const int cols = c8n < GN_THREADS ? c8n : GN_THREADS;
@@ -57,7 +62,7 @@ gn_fused_kernel(const float* __restrict__ x, const float* __restrict__ gamma, co
   for (int f = fi; f < F; f += wave) {
     const float* xb = x + (size_t)f * P * C;
     // ---- pass 1: per-thread column sums over this CTA's pixels
-    if (pl < PL) {
+    if (PHASE != 2 && pl < PL) {
       for (int c8 = col0; c8 < c8n; c8 += cols) {
         float s[8], q[8];
 #pragma unroll
@@ -96,7 +101,7 @@ gn_fused_kernel(const float* __restrict__ x, const float* __restrict__ gamma, co
     }
     __syncthreads();
     float* my_partial = partial + ((size_t)f * cpf + r) * GN_GROUPS * 2;
-    if (threadIdx.x < GN_GROUPS * 2) {
+    if (PHASE != 2 && threadIdx.x < GN_GROUPS * 2) {
       const int g = threadIdx.x >> 1, which = threadIdx.x & 1;
       float acc = 0.f;
       for (int l = 0; l < PL; ++l) {
@@ -107,13 +112,16 @@ gn_fused_kernel(const float* __restrict__ x, const float* __restrict__ gamma, co
       __threadfence();
     }
     __syncthreads();
-    // ---- frame barrier among the cpf CTAs of this frame
-    if (threadIdx.x == 0) {
-      atomicAdd(&g_gn_arrive[f], 1u);
-      while (*reinterpret_cast<volatile unsigned int*>(&g_gn_arrive[f]) < (unsigned int)cpf) __nanosleep(64);
-      __threadfence();
+    if (PHASE == 1) continue;
+    // ---- frame barrier among the cpf CTAs of this frame (each frame's counter is used exactly once per launch)
+    if (PHASE == 0) {
+      if (threadIdx.x == 0) {
+        atomicAdd(&arrive[f], 1u);
+        while (*reinterpret_cast<volatile unsigned int*>(&arrive[f]) < (unsigned int)cpf) __nanosleep(64);
+        __threadfence();
+      }
+      __syncthreads();
     }
-    __syncthreads();
     // ---- combine all partials of the frame (double precision, fixed order, identical in every CTA)
     {
       const int slot = threadIdx.x & 63, part = threadIdx.x >> 6;      // 8 interleaved partial sums per slot
@@ -123,10 +131,6 @@ gn_fused_kernel(const float* __restrict__ x, const float* __restrict__ gamma, co
       s_part[part][slot] = acc;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {     // every read of the counters and partials of this frame by this CTA is done
-      const unsigned int old = atomicAdd(&g_gn_depart[f], 1u);
-      if (old == (unsigned int)cpf - 1u) { g_gn_arrive[f] = 0u; g_gn_depart[f] = 0u; }
-    }
     if (threadIdx.x < GN_GROUPS) {
       const int g = threadIdx.x;
       double sm = 0.0, sq = 0.0;
@@ -148,8 +152,7 @@ gn_fused_kernel(const float* __restrict__ x, const float* __restrict__ gamma, co
     }
     __syncthreads();
     // ---- pass 2: normalise this CTA's pixel range (second read of x: L2)
-    __nv_bfloat16* yb = y + (size_t)f * P * C;
-    __nv_bfloat16* rb = raw ? raw + (size_t)f * P * C : nullptr;
+    const size_t row0 = (size_t)f * P;
     if (pl < PL) {
       for (int c8 = col0; c8 < c8n; c8 += cols) {
         float sc[8], sh[8];
@@ -157,17 +160,14 @@ gn_fused_kernel(const float* __restrict__ x, const float* __restrict__ gamma, co
         for (int j = 0; j < 8; ++j) { sc[j] = s_scale[c8 * 8 + j]; sh[j] = s_shift[c8 * 8 + j]; }
         auto emit = [&](size_t off, const float4& a, const float4& b) {
           float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-          if (rb) {
-            *reinterpret_cast<uint4*>(rb + off) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
-                                                              pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-          }
+          const size_t row = row0 + off / (size_t)C;
+          if (raw) store_op8<OP>(raw, row, C, c8 * 8, v);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float t = v[j] * sc[j] + sh[j];
             v[j] = act_silu ? silu(t) : t;
           }
-          *reinterpret_cast<uint4*>(yb + off) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
-                                                            pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+          store_op8<OP>(y, row, C, c8 * 8, v);
         };
         int p = p0 + pl;
         for (; p + 3 * PL < p1; p += 4 * PL) {      // four pixels in flight per thread
@@ -195,9 +195,9 @@ gn_fused_kernel(const float* __restrict__ x, const float* __restrict__ gamma, co
 // x: fp32 [b, T, P, C]. One block per (b, p); thread (t, g) = (warp, lane) owns the cpg channels of group g at frame t
 // and keeps them in registers: a single pass over HBM, exact two-pass statistics (mean, then centred sum of squares)
 // combined across the T warps through shared memory. Lanes read adjacent cpg-float runs, i.e. whole rows coalesced.
-template <int CPG>
+template <int CPG, int OP>
 __global__ void __launch_bounds__(512) gn_pixel_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                                       const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
+                                                       const float* __restrict__ beta, void* __restrict__ y,
                                                        int T, int P, int C, float eps, int act_silu) {
   __shared__ float red[16][32];
   const int t = threadIdx.x >> 5, g = threadIdx.x & 31;
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(512) gn_pixel_kernel(const float* __restrict__
   float qt = 0.f;
   for (int k = 0; k < T; ++k) qt += red[k][g];
   const float rstd = rsqrtf(qt / n + eps);
-  uint32_t* dst = reinterpret_cast<uint32_t*>(y + off);
+  const size_t row = ((size_t)b * T + t) * P + p;
   const float2* g2 = reinterpret_cast<const float2*>(gamma + g * CPG);
   const float2* b2 = reinterpret_cast<const float2*>(beta + g * CPG);
 #pragma unroll
@@ -241,15 +241,15 @@ __global__ void __launch_bounds__(512) gn_pixel_kernel(const float* __restrict__
     float a0 = (v[2 * j] - mean) * rstd * gm.x + bt.x;
     float a1 = (v[2 * j + 1] - mean) * rstd * gm.y + bt.y;
     if (act_silu) { a0 = silu(a0); a1 = silu(a1); }
-    dst[j] = pack_bf16x2(a0, a1);
+    store_op2<OP>(y, row, C, g * CPG + 2 * j, a0, a1);
   }
 }
 
 // ---------------------------------------------------------------- LayerNorm per token -> bf16
 // one warp per row; the row (C <= 2048 floats) lives in registers between the two passes.
-template <int MAXV>
+template <int MAXV, int OP>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                                        const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
+                                                        const float* __restrict__ beta, void* __restrict__ y,
                                                         long long rows, int C, float eps) {
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -281,7 +281,6 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
   const float rstd = rsqrtf(q / (float)C + eps);
-  uint2* yr = reinterpret_cast<uint2*>(y + row * C);
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const float4* b4 = reinterpret_cast<const float4*>(beta);
 #pragma unroll
@@ -293,7 +292,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
       const float o1 = (v[i].y - mean) * rstd * g.y + bb.y;
       const float o2 = (v[i].z - mean) * rstd * g.z + bb.z;
       const float o3 = (v[i].w - mean) * rstd * g.w + bb.w;
-      yr[j] = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+      const float o[4] = {o0, o1, o2, o3};
+      store_op4<OP>(y, (size_t)row, C, j * 4, o);
     }
   }
 }
@@ -322,17 +322,40 @@ static void gn_geometry(int64_t frames, int64_t pixels, int64_t channels, int* w
 extern "C" int64_t pn_groupnorm_workspace_floats(int64_t frames, int64_t pixels, int64_t channels) {
   int wave, cpf;
   gn_geometry(frames, pixels, channels, &wave, &cpf);
-  return frames * cpf * GN_GROUPS * 2;
+  return frames * cpf * GN_GROUPS * 2 + frames;      // partial sums + one arrival counter per frame
 }
 
-extern "C" int pn_groupnorm_silu(const float* x, const float* gamma, const float* beta, void* y_bf16,
-                                 void* raw_bf16, float* workspace, int64_t frames, int64_t pixels,
-                                 int64_t channels, float eps, int act_silu, void* stream_v) {
-  PN_REQUIRE(x && gamma && beta && y_bf16 && workspace, "pn_groupnorm_silu: null pointer");
+template <int OP, int PHASE>
+static int gn_launch(bool cooperative, int grid, size_t smem, cudaStream_t st, const float* x, const float* gamma, const float* beta,
+                     void* y, void* raw, float* partial, unsigned int* arrive, int P, int C, int F, int wave, int cpf, float eps,
+                     int act_silu) {
+  const int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&gn_fused_kernel<OP, PHASE>), smem);
+  if (rc != PN_OK) return rc;
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GN_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = cooperative ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gn_fused_kernel<OP, PHASE>, x, gamma, beta, y, raw, partial, arrive, P, C, F, wave, cpf,
+                                   eps, act_silu));
+  return PN_OK;
+}
+
+extern "C" int pn_groupnorm_silu(const float* x, const float* gamma, const float* beta, void* y, void* raw,
+                                 float* workspace, int64_t frames, int64_t pixels, int64_t channels, float eps,
+                                 int act_silu, int operand_mode, void* stream_v) {
+  PN_REQUIRE(x && gamma && beta && y && workspace, "pn_groupnorm_silu: null pointer");
   PN_REQUIRE(channels % 32 == 0 && channels % 8 == 0 && channels <= 8192, "pn_groupnorm_silu: C=%lld unsupported",
              (long long)channels);
   PN_REQUIRE(frames > 0 && pixels > 0, "pn_groupnorm_silu: empty input");
   PN_REQUIRE(frames <= GN_MAX_FRAMES, "pn_groupnorm_silu: more than %d frames", GN_MAX_FRAMES);
+  PN_REQUIRE(operand_mode >= 0 && operand_mode <= 2, "pn_groupnorm_silu: operand_mode %d", operand_mode);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
   const int P = (int)pixels, C = (int)channels, F = (int)frames;
   int wave, cpf;
@@ -341,35 +364,44 @@ extern "C" int pn_groupnorm_silu(const float* x, const float* gamma, const float
   const int cols = c8n < GN_THREADS ? c8n : GN_THREADS;
   const int PL = GN_THREADS / cols;
   const size_t smem = ((size_t)PL * 2 * C + 2 * (size_t)C) * sizeof(float);
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    PN_CHECK_CUDA(cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
+  float* partial = workspace;
+  unsigned int* arrive = reinterpret_cast<unsigned int*>(workspace + (size_t)F * cpf * GN_GROUPS * 2);
+  const int grid = wave * cpf;
+  // The fused form needs all wave * cpf CTAs resident at once. The grid never exceeds the SM count the device
+  // reports and the kernel takes one CTA per SM; the cooperative launch makes the runtime check that against what the
+  // context can really hold. PN_GN_TWO_PHASE=1 (or a single CTA per frame) selects the barrier-free two-launch form.
+  static const bool force_two_phase = [] { const char* e = std::getenv("PN_GN_TWO_PHASE"); return e && std::atoi(e) != 0; }();
+  if (force_two_phase) {
+    int rc = PN_OK;
+    PN_DISPATCH_OP(operand_mode, rc = gn_launch<OP, 1>(false, grid, smem, st, x, gamma, beta, y, raw, partial, arrive, P, C, F, wave,
+                                                        cpf, eps, act_silu));
+    if (rc != PN_OK) return rc;
+    PN_DISPATCH_OP(operand_mode, rc = gn_launch<OP, 2>(false, grid, smem, st, x, gamma, beta, y, raw, partial, arrive, P, C, F, wave,
+                                                        cpf, eps, act_silu));
+    return rc;
   }
-  // all wave * cpf CTAs spin on each other: they are co-resident because the grid never exceeds the SM count and the
-  // kernel is limited to one CTA per SM
-  gn_fused_kernel<<<wave * cpf, GN_THREADS, smem, st>>>(x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y_bf16),
-                                                        reinterpret_cast<__nv_bfloat16*>(raw_bf16), workspace, P, C, F,
-                                                        wave, cpf, eps, act_silu);
-  PN_CHECK_CUDA(cudaGetLastError());
-  return PN_OK;
+  PN_CHECK_CUDA(cudaMemsetAsync(arrive, 0, sizeof(unsigned int) * (size_t)F, st));
+  int rc = PN_OK;
+  PN_DISPATCH_OP(operand_mode, rc = gn_launch<OP, 0>(true, grid, smem, st, x, gamma, beta, y, raw, partial, arrive, P, C, F, wave,
+                                                      cpf, eps, act_silu));
+  return rc;
 }
 
-extern "C" int pn_groupnorm_pixel_silu(const float* x, const float* gamma, const float* beta, void* y_bf16,
+extern "C" int pn_groupnorm_pixel_silu(const float* x, const float* gamma, const float* beta, void* y,
                                        int64_t batch, int64_t frames_per_seq, int64_t pixels, int64_t channels,
-                                       float eps, int act_silu, void* stream_v) {
-  PN_REQUIRE(x && gamma && beta && y_bf16, "pn_groupnorm_pixel_silu: null pointer");
+                                       float eps, int act_silu, int operand_mode, void* stream_v) {
+  PN_REQUIRE(x && gamma && beta && y, "pn_groupnorm_pixel_silu: null pointer");
   PN_REQUIRE(channels % 64 == 0, "pn_groupnorm_pixel_silu: C=%lld must be a multiple of 64", (long long)channels);
   PN_REQUIRE(batch > 0 && frames_per_seq > 0 && pixels > 0, "pn_groupnorm_pixel_silu: empty input");
+  PN_REQUIRE(operand_mode >= 0 && operand_mode <= 2, "pn_groupnorm_pixel_silu: operand_mode %d", operand_mode);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
   PN_REQUIRE(frames_per_seq <= 16, "pn_groupnorm_pixel_silu: T=%lld > 16 unsupported", (long long)frames_per_seq);
   const long long blocks = batch * pixels;
   PN_REQUIRE(blocks < (1ll << 31), "pn_groupnorm_pixel_silu: grid too large");
   const int threads = (int)frames_per_seq * 32;
-  __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(y_bf16);
   const int T = (int)frames_per_seq, P = (int)pixels, C = (int)channels;
   switch (C / 32) {
-#define PN_GNP_CASE(CPG) case CPG: gn_pixel_kernel<CPG><<<(unsigned)blocks, threads, 0, st>>>(x, gamma, beta, y, T, P, C, eps, act_silu); break;
+#define PN_GNP_CASE(CPG) case CPG: PN_DISPATCH_OP(operand_mode, (gn_pixel_kernel<CPG, OP><<<(unsigned)blocks, threads, 0, st>>>(x, gamma, beta, y, T, P, C, eps, act_silu))); break;
     PN_GNP_CASE(2) PN_GNP_CASE(4) PN_GNP_CASE(6) PN_GNP_CASE(8) PN_GNP_CASE(10) PN_GNP_CASE(12) PN_GNP_CASE(16) PN_GNP_CASE(20)
     PN_GNP_CASE(24) PN_GNP_CASE(30) PN_GNP_CASE(32) PN_GNP_CASE(40) PN_GNP_CASE(60) PN_GNP_CASE(80)
 #undef PN_GNP_CASE
@@ -381,18 +413,18 @@ extern "C" int pn_groupnorm_pixel_silu(const float* x, const float* gamma, const
   return PN_OK;
 }
 
-extern "C" int pn_layernorm(const float* x, const float* gamma, const float* beta, void* y_bf16, int64_t rows,
-                            int64_t channels, float eps, void* stream_v) {
-  PN_REQUIRE(x && gamma && beta && y_bf16, "pn_layernorm: null pointer");
+extern "C" int pn_layernorm(const float* x, const float* gamma, const float* beta, void* y, int64_t rows,
+                            int64_t channels, float eps, int operand_mode, void* stream_v) {
+  PN_REQUIRE(x && gamma && beta && y, "pn_layernorm: null pointer");
   PN_REQUIRE(channels % 4 == 0 && channels <= 2048 && channels > 0, "pn_layernorm: C=%lld unsupported", (long long)channels);
   PN_REQUIRE(rows > 0, "pn_layernorm: empty input");
+  PN_REQUIRE(operand_mode >= 0 && operand_mode <= 2, "pn_layernorm: operand_mode %d", operand_mode);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
   const long long blocks = (rows * 32 + 255) / 256;
-  __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(y_bf16);
   const int C = (int)channels;
-  if (C <= 512) layernorm_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, beta, y, rows, C, eps);
-  else if (C <= 1024) layernorm_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, beta, y, rows, C, eps);
-  else layernorm_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, beta, y, rows, C, eps);
+  if (C <= 512) PN_DISPATCH_OP(operand_mode, (layernorm_kernel<4, OP><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, beta, y, rows, C, eps)));
+  else if (C <= 1024) PN_DISPATCH_OP(operand_mode, (layernorm_kernel<8, OP><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, beta, y, rows, C, eps)));
+  else PN_DISPATCH_OP(operand_mode, (layernorm_kernel<16, OP><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, beta, y, rows, C, eps)));
   PN_CHECK_CUDA(cudaGetLastError());
   return PN_OK;
 }

@@ -37,15 +37,17 @@ def temporal_pos_table(T: int, dim: int) -> torch.Tensor:
 
 
 class PackedWeights(dict):
-    """key -> packed device tensor (MMA-operand dtype for matrices, fp32 for biases / norm affine)."""
+    """key -> packed device tensor (MMA-operand dtype for matrices, fp32 for biases / norm affine).
+    `tag` ("unet" / "controlnet") names the network in the text-K/V cache."""
+    tag = ""
 
 
-def _pack_conv3(w, dt):      # [Cout, Cin, 3, 3] -> [Cout, (ky, kx, ci)]
-    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous().to(dt)
+def _conv3_matrix(w):      # [Cout, Cin, 3, 3] -> fp32 [Cout, (ky, kx, ci)]
+    return w.detach().to(F32).permute(0, 2, 3, 1).reshape(w.shape[0], -1)
 
 
-def _pack_conv1d(w, dt):     # [Cout, Cin, 3] -> [Cout, (k, ci)]
-    return w.permute(0, 2, 1).reshape(w.shape[0], -1).contiguous().to(dt)
+def _conv1d_matrix(w):     # [Cout, Cin, 3] -> fp32 [Cout, (k, ci)]
+    return w.detach().to(F32).permute(0, 2, 1).reshape(w.shape[0], -1)
 
 
 def _pack_direct(w, cin_pad=None):   # [Cout, Cin, 3, 3] -> fp32 [9, Cin_pad, Cout_pad16]
@@ -58,22 +60,28 @@ def _pack_direct(w, cin_pad=None):   # [Cout, Cin, 3, 3] -> fp32 [9, Cin_pad, Co
 
 
 class Engine:
-    def __init__(self, cfg: NetConfig, ops, op_dtype=torch.bfloat16):
+    """`ops` decides the precision mode: NativeOps (bf16 operands) or ParityOps (split-bf16 operands = fp32-class
+    products, fp32 attention). The engine only asks it how to pack a weight matrix (`pack_matrix`, `pack_small`), which
+    dtype attention inputs (`qkv_dtype`) and CUDA-core intermediates (`act_dtype`) have, and whether a GEMM epilogue can
+    emit the next operand directly (`fused_operand_emit`)."""
+
+    def __init__(self, cfg: NetConfig, ops):
         self.cfg = cfg
         self.ops = ops
-        self.dt = op_dtype
         self.plan_unet: Plan = make_plan(cfg, decoder=True)
         self.plan_cn: Plan = make_plan(cfg, decoder=False)
         self.wu: PackedWeights | None = None
         self.wc: PackedWeights | None = None
+        self.generation = 0
         self.cond = {"guided": None, "kv": {}, "b": None}     # step-invariant state (prepare_hint / prepare_text)
 
     # ------------------------------------------------------------------------------------------ packing
     def _pack_trunk(self, P: dict, plan: Plan) -> PackedWeights:
-        dt, f = self.dt, (lambda t: t.detach().to(F32).contiguous())
+        f = lambda t: t.detach().to(F32).contiguous()
+        mat, small = self.ops.pack_matrix, self.ops.pack_small
         W = PackedWeights()
-        W["te0.w"] = P["time_embed.0.weight"].detach().to(dt).contiguous(); W["te0.b"] = f(P["time_embed.0.bias"])
-        W["te2.w"] = P["time_embed.2.weight"].detach().to(dt).contiguous(); W["te2.b"] = f(P["time_embed.2.bias"])
+        W["te0.w"] = small(P["time_embed.0.weight"]); W["te0.b"] = f(P["time_embed.0.bias"])
+        W["te2.w"] = small(P["time_embed.2.weight"]); W["te2.b"] = f(P["time_embed.2.bias"])
         emb_w, emb_b, off = [], [], 0
         for st in plan.stages():
             k = st.key
@@ -82,14 +90,14 @@ class Engine:
             elif st.kind == "res":
                 for nm in ("in_layers.0", "in_layers_temporal.0", "out_layers.0", "out_layers_temporal.0"):
                     W[f"{k}.{nm}.g"] = f(P[f"{k}.{nm}.weight"]); W[f"{k}.{nm}.b"] = f(P[f"{k}.{nm}.bias"])
-                W[k + ".in.w"] = _pack_conv3(P[k + ".in_layers.2.weight"].detach(), dt); W[k + ".in.b"] = f(P[k + ".in_layers.2.bias"])
-                W[k + ".out.w"] = _pack_conv3(P[k + ".out_layers.3.weight"].detach(), dt); W[k + ".out.b"] = f(P[k + ".out_layers.3.bias"])
-                W[k + ".int.w"] = _pack_conv1d(P[k + ".in_layers_temporal.2.weight"].detach(), dt)
+                W[k + ".in.w"] = mat(_conv3_matrix(P[k + ".in_layers.2.weight"]), 9); W[k + ".in.b"] = f(P[k + ".in_layers.2.bias"])
+                W[k + ".out.w"] = mat(_conv3_matrix(P[k + ".out_layers.3.weight"]), 9); W[k + ".out.b"] = f(P[k + ".out_layers.3.bias"])
+                W[k + ".int.w"] = mat(_conv1d_matrix(P[k + ".in_layers_temporal.2.weight"]), 3)
                 W[k + ".int.b"] = f(P[k + ".in_layers_temporal.2.bias"])
-                W[k + ".outt.w"] = _pack_conv1d(P[k + ".out_layers_temporal.3.weight"].detach(), dt)
+                W[k + ".outt.w"] = mat(_conv1d_matrix(P[k + ".out_layers_temporal.3.weight"]), 3)
                 W[k + ".outt.b"] = f(P[k + ".out_layers_temporal.3.bias"])
                 if st.cin != st.cout:
-                    W[k + ".skip.w"] = P[k + ".skip_connection.weight"].detach().reshape(st.cout, st.cin).to(dt).contiguous()
+                    W[k + ".skip.w"] = mat(P[k + ".skip_connection.weight"].detach().reshape(st.cout, st.cin))
                     W[k + ".skip.b"] = f(P[k + ".skip_connection.bias"])
                 emb_w.append(P[k + ".emb_layers.1.weight"].detach()); emb_b.append(P[k + ".emb_layers.1.bias"].detach())
                 W[k + ".emb_off"] = off
@@ -99,43 +107,46 @@ class Engine:
                 for br in STT_BRANCHES:
                     W[f"{k}.norm{br}.g"] = f(P[f"{k}.norm{br}.weight"]); W[f"{k}.norm{br}.b"] = f(P[f"{k}.norm{br}.bias"])
                     for pj in ("proj_in", "proj_out"):
-                        W[f"{k}.{pj}{br}.w"] = P[f"{k}.{pj}{br}.weight"].detach().to(dt).contiguous()
+                        W[f"{k}.{pj}{br}.w"] = mat(P[f"{k}.{pj}{br}.weight"])
                         W[f"{k}.{pj}{br}.b"] = f(P[f"{k}.{pj}{br}.bias"])
                     t = f"{k}.transformer_blocks{br}.0"
                     for nm in ("norm1", "norm2", "norm3"):
                         W[f"{t}.{nm}.g"] = f(P[f"{t}.{nm}.weight"]); W[f"{t}.{nm}.b"] = f(P[f"{t}.{nm}.bias"])
-                    W[t + ".qkv.w"] = torch.cat([P[f"{t}.attn1.to_{n}.weight"].detach() for n in "qkv"], 0).to(dt).contiguous()
-                    W[t + ".q2.w"] = P[t + ".attn2.to_q.weight"].detach().to(dt).contiguous()
-                    W[t + ".kv2.w"] = torch.cat([P[t + ".attn2.to_k.weight"].detach(), P[t + ".attn2.to_v.weight"].detach()], 0).to(dt).contiguous()
+                    W[t + ".qkv.w"] = mat(torch.cat([P[f"{t}.attn1.to_{n}.weight"].detach() for n in "qkv"], 0))
+                    W[t + ".q2.w"] = mat(P[t + ".attn2.to_q.weight"])
+                    W[t + ".kv2.w"] = mat(torch.cat([P[t + ".attn2.to_k.weight"].detach(), P[t + ".attn2.to_v.weight"].detach()], 0))
                     for a in ("attn1", "attn2"):
-                        W[f"{t}.{a}.o.w"] = P[f"{t}.{a}.to_out.0.weight"].detach().to(dt).contiguous()
+                        W[f"{t}.{a}.o.w"] = mat(P[f"{t}.{a}.to_out.0.weight"])
                         W[f"{t}.{a}.o.b"] = f(P[f"{t}.{a}.to_out.0.bias"])
                     # GEGLU: 16 value rows then their 16 gate rows, so one accumulator chunk holds both halves
                     w1, b1 = P[t + ".ff.net.0.proj.weight"].detach(), P[t + ".ff.net.0.proj.bias"].detach()
-                    W[t + ".ff1.w"] = geglu_pack(w1).to(dt).contiguous()
+                    W[t + ".ff1.w"] = mat(geglu_pack(w1))
                     W[t + ".ff1.b"] = geglu_pack(b1).to(F32).contiguous()
-                    W[t + ".ff2.w"] = P[t + ".ff.net.2.weight"].detach().to(dt).contiguous(); W[t + ".ff2.b"] = f(P[t + ".ff.net.2.bias"])
+                    W[t + ".ff2.w"] = mat(P[t + ".ff.net.2.weight"]); W[t + ".ff2.b"] = f(P[t + ".ff.net.2.bias"])
             elif st.kind == "down":
-                W[k + ".w"] = _pack_conv3(P[k + ".op.weight"].detach(), dt); W[k + ".b"] = f(P[k + ".op.bias"])
+                W[k + ".w"] = mat(_conv3_matrix(P[k + ".op.weight"]), 9); W[k + ".b"] = f(P[k + ".op.bias"])
             elif st.kind == "up":
-                W[k + ".w"] = _pack_conv3(P[k + ".conv.weight"].detach(), dt); W[k + ".b"] = f(P[k + ".conv.bias"])
-        W["emb.w"] = torch.cat(emb_w, 0).to(dt).contiguous()
+                W[k + ".w"] = mat(_conv3_matrix(P[k + ".conv.weight"]), 9); W[k + ".b"] = f(P[k + ".conv.bias"])
+        W["emb.w"] = small(torch.cat(emb_w, 0))
         W["emb.b"] = torch.cat(emb_b, 0).to(F32).contiguous()
         return W
 
     def pack(self, unet_params: dict | None, cn_params: dict | None) -> None:
         """(Re)build packed weights from fp32 parameters keyed by the reference's state-dict names
         (ControlledUNetModel3D's own keys / ControlNet3D's keys, without prefixes). Either may be None."""
-        cfg, dt = self.cfg, self.dt
+        cfg = self.cfg
         f = lambda t: t.detach().to(F32).contiguous()
         self.wu = self.wc = None
+        self.generation = getattr(self, "generation", 0) + 1      # monotonically increasing: cache / graph signatures key on it
         if unet_params is not None:
             wu = self._pack_trunk(unet_params, self.plan_unet)
+            wu.tag = "unet"
             wu["out.g"] = f(unet_params["out.0.weight"]); wu["out.bn"] = f(unet_params["out.0.bias"])
             wu["out.w"] = _pack_direct(unet_params["out.2.weight"].detach()); wu["out.b"] = f(unet_params["out.2.bias"])
             self.wu = wu
         if cn_params is not None:
             wc = self._pack_trunk(cn_params, self.plan_cn)
+            wc.tag = "controlnet"
             for i in range(len(HINT_STRIDES)):
                 w = cn_params[f"input_hint_block.{2 * i}.weight"].detach()
                 wc[f"hint{i}.w"] = _pack_direct(w, cin_pad=(w.shape[1] + 3) // 4 * 4)
@@ -144,7 +155,7 @@ class Engine:
             names = [f"zero_convs.{i}.0" for i in range(len(self.plan_cn.skip_channels))] + ["middle_block_out.0"]
             for i, nm in enumerate(names):
                 w = cn_params[nm + ".weight"].detach()
-                wc[f"zc{i}.w"] = (w.reshape(w.shape[0], w.shape[1]) * s).to(dt).contiguous()
+                wc[f"zc{i}.w"] = self.ops.pack_matrix(w.reshape(w.shape[0], w.shape[1]).to(F32) * s)
                 wc[f"zc{i}.b"] = (cn_params[nm + ".bias"].detach().to(F32) * s).contiguous()
             self.wc = wc
         self.cond = {"guided": None, "kv": {}, "b": None}
@@ -153,7 +164,8 @@ class Engine:
     def prepare_hint(self, hint_nchw: torch.Tensor, hint_repeat: int = 1) -> None:
         """BEV hint stem, once per sample (controlmodel.py:43-59,118). hint_nchw fp32
         [frames/hint_repeat, hint_channels, 8H, 8W]; under CFG both halves share the hint (hint_repeat=2)."""
-        ops, dt, wc = self.ops, self.dt, self.wc
+        ops, wc = self.ops, self.wc
+        dt = ops.act_dtype
         assert wc is not None, "pack() the ControlNet parameters first"
         Fh, Ch, Hh, Wh = hint_nchw.shape
         cin_pad = wc["hint0.w"].shape[1]
@@ -176,7 +188,8 @@ class Engine:
     def prepare_text(self, context: torch.Tensor) -> None:
         """K/V projections of the text context for every attn2 (attention.py:248-250), once per sample.
         context fp32 [b, L<=128, context_dim]."""
-        ops, dt = self.ops, self.dt
+        ops = self.ops
+        dt = ops.qkv_dtype
         b, L, D = context.shape
         ctx = self._to_operand(context.to(F32).contiguous().reshape(b * L, D))
         kv = self.cond["kv"]
@@ -188,11 +201,11 @@ class Engine:
                     continue
                 for br in STT_BRANCHES:
                     t = f"{st.key}.transformer_blocks{br}.0"
-                    old = kv.get((id(W), t))
+                    old = kv.get((W.tag, t))
                     if old is not None and old.shape == (b, L, 2 * st.cin):
                         ops.gemm(ctx, W[t + ".kv2.w"], out_dtype=dt, out=old.view(b * L, 2 * st.cin))   # same address
                     else:
-                        kv[(id(W), t)] = ops.gemm(ctx, W[t + ".kv2.w"], out_dtype=dt).reshape(b, L, 2 * st.cin)
+                        kv[(W.tag, t)] = ops.gemm(ctx, W[t + ".kv2.w"], out_dtype=dt).reshape(b, L, 2 * st.cin)
         self.cond["b"] = b
 
     def prepare_condition(self, hint_nchw: torch.Tensor, context: torch.Tensor, hint_repeat: int = 1) -> None:
@@ -211,7 +224,7 @@ class Engine:
 
     def _res(self, W, st: Stage, x, embv):
         """ResBlock3D._forward (openaimodel.py:499-542)."""
-        ops, dt, k, T = self.ops, self.dt, st.key, self.cfg.num_frames
+        ops, k, T = self.ops, st.key, self.cfg.num_frames
         Fr, H, Wd, _ = x.shape
         b, P, C = Fr // T, H * Wd, st.cout
         need_skip = st.cin != st.cout
@@ -233,7 +246,8 @@ class Engine:
 
     def _transformer(self, W, t: str, y, heads, mode, geom, kv):
         """BasicTransformerBlock._forward (attention.py:726-747) on the fp32 token stream y [tokens, C]."""
-        ops, dt = self.ops, self.dt
+        ops = self.ops
+        dt = ops.qkv_dtype
         Fr, H, Wd, C, b, T = geom
         n1 = ops.layernorm(y, W[t + ".norm1.g"], W[t + ".norm1.b"])
         qkv = ops.gemm(n1, W[t + ".qkv.w"], out_dtype=dt)
@@ -242,16 +256,16 @@ class Engine:
         else:
             V = self.cfg.num_views
             o = ops.attention_view(qkv.view(Fr, H, V, Wd // V, 3 * C), heads, mode == "cross", CROSS_VIEW_NEIGHBOURS)
-        y = ops.gemm(o.view(-1, C), W[t + ".attn1.o.w"], bias=W[t + ".attn1.o.b"], residual=y, out=y)
+        y = ops.gemm(o.view(-1, o.shape[-1]), W[t + ".attn1.o.w"], bias=W[t + ".attn1.o.b"], residual=y, out=y)
         n2 = ops.layernorm(y, W[t + ".norm2.g"], W[t + ".norm2.b"])
         q = ops.gemm(n2, W[t + ".q2.w"], out_dtype=dt)
         o = ops.attention_text(q.view(b, T * H * Wd, C), kv, heads)
-        y = ops.gemm(o.view(-1, C), W[t + ".attn2.o.w"], bias=W[t + ".attn2.o.b"], residual=y, out=y)
+        y = ops.gemm(o.view(-1, o.shape[-1]), W[t + ".attn2.o.w"], bias=W[t + ".attn2.o.b"], residual=y, out=y)
         n3 = ops.layernorm(y, W[t + ".norm3.g"], W[t + ".norm3.b"])
-        ff = ops.gemm(n3, W[t + ".ff1.w"], bias=W[t + ".ff1.b"], geglu=True, out_dtype=dt)
+        ff = ops.gemm(n3, W[t + ".ff1.w"], bias=W[t + ".ff1.b"], geglu=True, out_dtype=ops.act_dtype)
         # the block's output is only ever consumed as the bf16 operand of proj_out: emit it in that form directly
         # (saves the fp32 write, the cast kernel's fp32 read and one launch per transformer block)
-        if self.dt == torch.bfloat16:
+        if ops.fused_operand_emit:
             return ops.gemm(ff, W[t + ".ff2.w"], bias=W[t + ".ff2.b"], residual=y, out_dtype=torch.bfloat16)
         return ops.gemm(ff, W[t + ".ff2.w"], bias=W[t + ".ff2.b"], residual=y, out=y)
 
@@ -265,18 +279,18 @@ class Engine:
             a = ops.groupnorm(x, W[f"{k}.norm{br}.g"], W[f"{k}.norm{br}.b"], 1e-6, False)
             if mode == "temporal":
                 pe = self._pos_table(T, C, x.device)
-                y = ops.gemm(a.view(-1, C), W[f"{k}.proj_in{br}.w"], bias=W[f"{k}.proj_in{br}.b"], rowvec=pe,
+                y = ops.gemm(a.view(-1, a.shape[-1]), W[f"{k}.proj_in{br}.w"], bias=W[f"{k}.proj_in{br}.b"], rowvec=pe,
                              rows_per_group=H * Wd, n_groups=T)
             else:
-                y = ops.gemm(a.view(-1, C), W[f"{k}.proj_in{br}.w"], bias=W[f"{k}.proj_in{br}.b"])
+                y = ops.gemm(a.view(-1, a.shape[-1]), W[f"{k}.proj_in{br}.w"], bias=W[f"{k}.proj_in{br}.b"])
             t = f"{k}.transformer_blocks{br}.0"
-            y = self._transformer(W, t, y, st.heads, mode, geom, self.cond["kv"][(id(W), t)])
-            yb = y if y.dtype == self.dt else self._to_operand(y)
+            y = self._transformer(W, t, y, st.heads, mode, geom, self.cond["kv"][(W.tag, t)])
+            yb = self._to_operand(y) if y.dtype == F32 else y
             x = ops.gemm(yb, W[f"{k}.proj_out{br}.w"], bias=W[f"{k}.proj_out{br}.b"], residual=x, out=x).view(Fr, H, Wd, C)
         return x
 
     def _to_operand(self, y):
-        return self.ops.cast_bf16(y) if self.dt == torch.bfloat16 else y.to(self.dt)
+        return self.ops.cast_operand(y)
 
     def _pos_table(self, T, C, device):
         key = (T, C, str(device))
@@ -335,7 +349,7 @@ class Engine:
             skip = hs.pop()
             h = ops.concat_add(h, skip, control.pop().view(skip.shape))
             h = self._run_block(W, blk, h, embv)
-        a = ops.groupnorm(h, W["out.g"], W["out.bn"], 1e-5, True)
+        a = ops.groupnorm(h, W["out.g"], W["out.bn"], 1e-5, True, out_f32=ops.act_dtype == F32)
         return ops.conv3x3_direct(a, W["out.w"], W["out.b"], self.cfg.out_channels)
 
     def eps(self, x_nchw, concat_nchw, t):

@@ -13,6 +13,7 @@ from . import _lib
 
 BF16 = torch.bfloat16
 F32 = torch.float32
+OP_BF16, OP_SPLIT3, OP_F32 = 0, 1, 2      # include/panacea_b200.h pn_operand_mode
 
 
 def _ptr(t):
@@ -39,12 +40,47 @@ def geglu_pack(t: torch.Tensor) -> torch.Tensor:
     return torch.stack([v, g], 1).reshape(t.shape).contiguous()
 
 
+def split3(t: torch.Tensor, taps: int = 1) -> torch.Tensor:
+    """Parity-mode packing of a WEIGHT matrix [N, taps*C] (fp32) -> bf16 [N, taps*3C]: per tap [W_hi | W_hi | W_lo] with
+    W_hi = bf16(W), W_lo = bf16(W - W_hi). Against an activation operand stored [a_hi | a_lo | a_hi] (operand.cuh)
+    the bf16 GEMM then computes a_hi W_hi + a_lo W_hi + a_hi W_lo = a W up to 2^-18 relative."""
+    n, k = t.shape
+    w = t.detach().to(F32).reshape(n, taps, k // taps)
+    hi = w.to(BF16)
+    lo = (w - hi.to(F32)).to(BF16)
+    return torch.cat([hi, hi, lo], dim=2).reshape(n, 3 * k).contiguous()
+
+
 class NativeOps:
-    """The production op set. `launches` counts kernel launches issued through the C ABI."""
+    """The production op set (bf16 operands). `launches` counts kernel launches issued through the C ABI.
+    `operand_mode` / `operand_mult` describe how producers store GEMM operands (ParityOps overrides them)."""
+
+    operand_mode = OP_BF16
+    operand_mult = 1          # operand row width = operand_mult * C
+    qkv_dtype = BF16          # dtype of attention inputs
+    act_dtype = BF16          # dtype of intermediates consumed by CUDA-core kernels (hint stem, GEGLU output, head input)
+    fused_operand_emit = True # a GEMM epilogue may store the next GEMM's operand directly (out_dtype=bf16)
 
     def __init__(self):
         self.lib = _lib.load()
         self.launches = 0
+        self._freqs = {}
+
+    def pack_matrix(self, w: torch.Tensor, taps: int = 1) -> torch.Tensor:
+        """fp32 weight [N, taps*C] -> the B operand pn_gemm reads in this op set's precision mode."""
+        return w.detach().to(BF16).contiguous()
+
+    def pack_small(self, w: torch.Tensor) -> torch.Tensor:
+        """weight of the M<=32 time-embedding linears (pn_linear_small)."""
+        return w.detach().to(BF16).contiguous()
+
+    def _operand_empty(self, shape, device, mode=None):
+        mode = self.operand_mode if mode is None else mode
+        if mode == OP_F32:
+            return torch.empty(shape, device=device, dtype=F32)
+        if mode == OP_SPLIT3:
+            return torch.empty((*shape[:-1], 3 * shape[-1]), device=device, dtype=BF16)
+        return torch.empty(shape, device=device, dtype=BF16)
 
     # ------------------------------------------------------------------ GEMM / implicit conv
     def gemm(self, a, w, *, bias=None, rowvec=None, rows_per_group=0, n_groups=0, residual=None, residual2=None,
@@ -123,27 +159,29 @@ class NativeOps:
         return out.reshape(*lead, n_out) if out.is_contiguous() else out
 
     # ------------------------------------------------------------------ normalisation
-    def groupnorm(self, x, gamma, beta, eps, silu, want_raw=False):
-        """x fp32 [F, P, C] (or [F,H,W,C]) -> bf16 same shape; statistics over (C/32, all pixels of a frame)."""
+    def groupnorm(self, x, gamma, beta, eps, silu, want_raw=False, out_f32=False):
+        """x fp32 [F, P, C] (or [F,H,W,C]) -> operand of the same shape (bf16; [.., 3C] in parity mode; fp32 when
+        out_f32, for a CUDA-core consumer); statistics over (C/32, all pixels of a frame)."""
         _req(x.is_cuda and x.dtype == F32 and x.is_contiguous(), "groupnorm: x must be contiguous CUDA fp32")
         Fr, Cc = x.shape[0], x.shape[-1]
         P = x.numel() // (Fr * Cc)
-        y = torch.empty(x.shape, device=x.device, dtype=BF16)
-        raw = torch.empty(x.shape, device=x.device, dtype=BF16) if want_raw else None
+        mode = OP_F32 if out_f32 else self.operand_mode
+        y = self._operand_empty(x.shape, x.device, mode)
+        raw = self._operand_empty(x.shape, x.device, mode) if want_raw else None
         nws = self.lib.pn_groupnorm_workspace_floats(Fr, P, Cc)
         ws = torch.empty(nws, device=x.device, dtype=F32)
         _lib.check(self.lib.pn_groupnorm_silu(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(raw), _ptr(ws), Fr, P, Cc,
-                                             float(eps), int(bool(silu)), _stream()), "pn_groupnorm_silu")
-        self.launches += 1
+                                             float(eps), int(bool(silu)), mode, _stream()), "pn_groupnorm_silu")
+        self.launches += 2        # counter memset + kernel
         return (y, raw) if want_raw else y
 
     def groupnorm_pixel(self, x, gamma, beta, eps, silu):
         """x fp32 [b, T, P, C] -> bf16; statistics over (C/32, T) per pixel (temporal branch of ResBlock3D)."""
         _req(x.is_cuda and x.dtype == F32 and x.is_contiguous() and x.dim() == 4, "groupnorm_pixel: x fp32 [b,T,P,C]")
         b, T, P, Cc = x.shape
-        y = torch.empty(x.shape, device=x.device, dtype=BF16)
+        y = self._operand_empty(x.shape, x.device)
         _lib.check(self.lib.pn_groupnorm_pixel_silu(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), b, T, P, Cc, float(eps),
-                                                   int(bool(silu)), _stream()), "pn_groupnorm_pixel_silu")
+                                                   int(bool(silu)), self.operand_mode, _stream()), "pn_groupnorm_pixel_silu")
         self.launches += 1
         return y
 
@@ -151,9 +189,9 @@ class NativeOps:
         _req(x.is_cuda and x.dtype == F32 and x.is_contiguous(), "layernorm: x must be contiguous CUDA fp32")
         Cc = x.shape[-1]
         rows = x.numel() // Cc
-        y = torch.empty(x.shape, device=x.device, dtype=BF16)
-        _lib.check(self.lib.pn_layernorm(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), rows, Cc, float(eps), _stream()),
-                   "pn_layernorm")
+        y = self._operand_empty(x.shape, x.device)
+        _lib.check(self.lib.pn_layernorm(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), rows, Cc, float(eps), self.operand_mode,
+                                         _stream()), "pn_layernorm")
         self.launches += 1
         return y
 
@@ -234,16 +272,16 @@ class NativeOps:
         _req(x.is_cuda and x.dtype == F32 and x.is_contiguous() and x.dim() == 4, "im2col_s2: x fp32 [F,H,W,C]")
         Fr, H, W, Cc = x.shape
         Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
-        out = torch.empty((Fr * Ho * Wo, 9 * Cc), device=x.device, dtype=BF16)
-        _lib.check(self.lib.pn_im2col3x3_s2(_ptr(x), _ptr(out), Fr, H, W, Cc, _stream()), "pn_im2col3x3_s2")
+        out = torch.empty((Fr * Ho * Wo, 9 * self.operand_mult * Cc), device=x.device, dtype=BF16)
+        _lib.check(self.lib.pn_im2col3x3_s2(_ptr(x), _ptr(out), Fr, H, W, Cc, self.operand_mode, _stream()), "pn_im2col3x3_s2")
         self.launches += 1
         return out, (Fr, Ho, Wo)
 
     def upsample2x(self, x):
         _req(x.is_cuda and x.dtype == F32 and x.is_contiguous() and x.dim() == 4, "upsample2x: x fp32 [F,H,W,C]")
         Fr, H, W, Cc = x.shape
-        y = torch.empty((Fr, 2 * H, 2 * W, Cc), device=x.device, dtype=BF16)
-        _lib.check(self.lib.pn_upsample2x_bf16(_ptr(x), _ptr(y), Fr, H, W, Cc, _stream()), "pn_upsample2x_bf16")
+        y = self._operand_empty((Fr, 2 * H, 2 * W, Cc), x.device)
+        _lib.check(self.lib.pn_upsample2x(_ptr(x), _ptr(y), Fr, H, W, Cc, self.operand_mode, _stream()), "pn_upsample2x")
         self.launches += 1
         return y
 
@@ -263,10 +301,12 @@ class NativeOps:
         self.launches += 1
         return x
 
-    def cast_bf16(self, x):
-        _req(x.dtype == F32 and x.is_contiguous(), "cast_bf16: fp32 contiguous")
-        y = torch.empty(x.shape, device=x.device, dtype=BF16)
-        _lib.check(self.lib.pn_cast_bf16(_ptr(x), _ptr(y), x.numel(), _stream()), "pn_cast_bf16")
+    def cast_operand(self, x):
+        """fp32 [..., C] -> GEMM operand (bf16 [..., C]; [..., 3C] in parity mode)."""
+        _req(x.dtype == F32 and x.is_contiguous(), "cast_operand: fp32 contiguous")
+        Cc = x.shape[-1]
+        y = self._operand_empty(x.shape, x.device)
+        _lib.check(self.lib.pn_cast_operand(_ptr(x), _ptr(y), x.numel() // Cc, Cc, self.operand_mode, _stream()), "pn_cast_operand")
         self.launches += 1
         return y
 
@@ -291,18 +331,25 @@ class NativeOps:
     def timestep_embedding(self, t, dim):
         _req(t.is_cuda and t.dtype == torch.int64 and t.is_contiguous(), "timestep_embedding: t must be CUDA int64")
         out = torch.empty((t.numel(), dim), device=t.device, dtype=F32)
-        _lib.check(self.lib.pn_timestep_embedding(_ptr(t), _ptr(out), t.numel(), dim, _stream()), "pn_timestep_embedding")
+        key = (dim, t.device)
+        if key not in self._freqs:
+            # the reference's own expression on the host (util.py:236-240), so t * f is bit-identical to the reference's
+            import math
+            half = dim // 2
+            self._freqs[key] = torch.exp(-math.log(10000) * torch.arange(start=0, end=half, dtype=F32) / half).to(t.device)
+        _lib.check(self.lib.pn_timestep_embedding(_ptr(t), _ptr(out), t.numel(), dim, _ptr(self._freqs[key]), _stream()),
+                   "pn_timestep_embedding")
         self.launches += 1
         return out
 
     def linear_small(self, x, w, bias, silu_in=False, silu_out=False):
-        """x fp32 [M<=32, K]; w bf16 [N, K]; -> fp32 [M, N]."""
-        _req(x.dtype == F32 and x.is_contiguous() and w.dtype == BF16 and w.is_contiguous(), "linear_small: dtypes")
+        """x fp32 [M<=32, K]; w bf16 or fp32 [N, K]; -> fp32 [M, N]."""
+        _req(x.dtype == F32 and x.is_contiguous() and w.dtype in (BF16, F32) and w.is_contiguous(), "linear_small: dtypes")
         M, K = x.shape
         N = w.shape[0]
         y = torch.empty((M, N), device=x.device, dtype=F32)
-        _lib.check(self.lib.pn_linear_small(_ptr(x), _ptr(w), _ptr(bias), _ptr(y), M, N, K, N, int(silu_in), int(silu_out),
-                                           _stream()), "pn_linear_small")
+        _lib.check(self.lib.pn_linear_small(_ptr(x), _ptr(w), int(w.dtype == F32), _ptr(bias), _ptr(y), M, N, K, N, int(silu_in),
+                                           int(silu_out), _stream()), "pn_linear_small")
         self.launches += 1
         return y
 
@@ -316,9 +363,104 @@ class NativeOps:
         self.launches += 1
         return x
 
+    def fingerprint(self, x):
+        """(sum, weighted sum) of the 32-bit words of a contiguous CUDA tensor, as Python ints (synchronises)."""
+        _req(x.is_cuda and x.is_contiguous() and (x.numel() * x.element_size()) % 4 == 0, "fingerprint: contiguous CUDA tensor")
+        out = torch.empty(2, device=x.device, dtype=torch.int64)
+        _lib.check(self.lib.pn_fingerprint(_ptr(x), x.numel() * x.element_size(), _ptr(out), _stream()), "pn_fingerprint")
+        self.launches += 1
+        a, b = out.tolist()
+        return (a, b, tuple(x.shape), x.dtype)
+
     def scale_dup(self, x, s, copies):
         _req(x.dtype == F32 and x.is_contiguous(), "scale_dup: fp32 contiguous")
         out = torch.empty((copies * x.shape[0], *x.shape[1:]), device=x.device, dtype=F32)
         _lib.check(self.lib.pn_scale_dup(_ptr(x), _ptr(out), x.numel(), float(s), copies, _stream()), "pn_scale_dup")
+        self.launches += 1
+        return out
+
+
+class ParityOps(NativeOps):
+    """fp32-class precision mode (the literal rtol 1e-3 / atol 1e-4 bar of BASELINE.json against the reference's fp32
+    math). Same kernels, different operand encoding: every producer stores the GEMM operand as bf16 [hi | lo | hi]
+    (3C wide), weights are packed [W_hi | W_hi | W_lo], so the tcgen05 GEMM/conv kernel computes fp32-class products by
+    K-concatenation; attention runs in fp32 on CUDA cores (pn_attention_f32); GEGLU uses the exact erf; the
+    time-embedding linears read fp32 weights. About 3-4x the cost of the bf16 path."""
+
+    operand_mode = OP_SPLIT3
+    operand_mult = 3
+    qkv_dtype = F32
+    act_dtype = F32
+    fused_operand_emit = False
+
+    def pack_matrix(self, w, taps=1):
+        return split3(w, taps)
+
+    def pack_small(self, w):
+        return w.detach().to(F32).contiguous()
+
+    def gemm(self, a, w, *, geglu=False, out_dtype=F32, **kw):
+        if geglu:
+            # fp32 GEMM output in the packed (16 value | 16 gate) column layout, then the exact-erf GEGLU as its own pass
+            _req(kw.get("residual") is None and kw.get("out") is None, "parity gemm: GEGLU takes no residual / out")
+            h = super().gemm(a, w, out_dtype=F32, **kw)
+            inner = h.shape[-1] // 2
+            rows = h.numel() // h.shape[-1]
+            y = self._operand_empty((*h.shape[:-1], inner), h.device)
+            _lib.check(self.lib.pn_geglu_operand(_ptr(h), _ptr(y), rows, inner, self.operand_mode, _stream()), "pn_geglu_operand")
+            self.launches += 1
+            return y
+        _req(out_dtype == F32, "parity gemm: outputs are fp32 (operands are produced by cast_operand)")
+        return super().gemm(a, w, out_dtype=F32, **kw)
+
+    # ------------------------------------------------------------------ attention (fp32, CUDA cores)
+    def _attention_f32(self, q, k, v, out, *, q_ld, kv_ld, F, H, V, W, Hk, Vk, Wk, heads, head_dim, views):
+        a = _lib.AttnArgs()
+        a.q, a.k, a.v, a.out = q, k, v, out
+        a.q_ld, a.kv_ld, a.out_ld = q_ld, kv_ld, heads * head_dim
+        a.F, a.H, a.V, a.W = F, H, V, W
+        a.Hk, a.Vk, a.Wk = Hk, Vk, Wk
+        a.kv_frame_div = 1
+        a.heads, a.head_dim = heads, head_dim
+        for vi, lst in enumerate(views):
+            a.kv_view_count[vi] = len(lst)
+            for j, kvv in enumerate(lst):
+                a.kv_views[vi][j] = kvv
+        a.scale = head_dim ** -0.5
+        _lib.check(self.lib.pn_attention_f32(C.byref(a), self.operand_mode, _stream()), "pn_attention_f32")
+        self.launches += 1
+
+    def attention_view(self, qkv, heads, cross, neighbours):
+        _req(qkv.is_cuda and qkv.dtype == F32 and qkv.is_contiguous() and qkv.dim() == 5, "attention_view(parity): qkv fp32 [F,H,V,w,3C]")
+        Fr, H, V, w, C3 = qkv.shape
+        Cc = C3 // 3
+        d = Cc // heads
+        out = self._operand_empty((Fr, H, V, w, Cc), qkv.device)
+        views = [list(neighbours[v]) for v in range(V)] if cross else [[v] for v in range(V)]
+        base = qkv.data_ptr()
+        self._attention_f32(base, base + 4 * Cc, base + 8 * Cc, out.data_ptr(), q_ld=C3, kv_ld=C3, F=Fr, H=H, V=V, W=w, Hk=H, Vk=V, Wk=w,
+                            heads=heads, head_dim=d, views=views)
+        return out
+
+    def attention_text(self, q, kv, heads):
+        _req(q.is_cuda and q.dtype == F32 and q.is_contiguous() and kv.dtype == F32 and kv.is_contiguous(), "attention_text(parity): fp32")
+        b, Nq, Cc = q.shape
+        Nk = kv.shape[1]
+        _req(kv.shape[0] == b and kv.shape[2] == 2 * Cc, "attention_text: bad shapes")
+        out = self._operand_empty((b, Nq, Cc), q.device)
+        base = kv.data_ptr()
+        self._attention_f32(q.data_ptr(), base, base + 4 * Cc, out.data_ptr(), q_ld=Cc, kv_ld=2 * Cc, F=b, H=1, V=1, W=Nq, Hk=1, Vk=1,
+                            Wk=Nk, heads=heads, head_dim=Cc // heads, views=[[0]])
+        return out
+
+    def attention_temporal(self, qkv, heads):
+        _req(qkv.is_cuda and qkv.dtype == F32 and qkv.is_contiguous() and qkv.dim() == 4, "attention_temporal(parity): qkv fp32 [b,T,P,3C]")
+        b, T, P, C3 = qkv.shape
+        Cc = C3 // 3
+        d = Cc // heads
+        out = self._operand_empty((b, T, P, Cc), qkv.device)
+        base = qkv.data_ptr()
+        _lib.check(self.lib.pn_attention_temporal_f32(base, base + 4 * Cc, base + 8 * Cc, out.data_ptr(), b, T, P, heads, d, C3, d ** -0.5,
+                                                     self.operand_mode, _stream()), "pn_attention_temporal_f32")
         self.launches += 1
         return out

@@ -49,8 +49,10 @@ class DenoisingPipeline:
     (diffusion.py:65-95) minus conditioner / first stage (out of scope)."""
 
     def __init__(self, network_config=None, denoiser_config=None, sampler_config=None, use_cuda_graph=True,
-                 share_noise_level: float = 0.07):
+                 share_noise_level: float = 0.07, precision: str | None = None):
         self.model = instantiate_from_config(network_config or default_network_config())
+        if precision is not None:
+            self.model.set_precision(precision)
         self.wrapper = OpenAIWrapperControlLDM3D(self.model, use_cuda_graph=use_cuda_graph)
         self.denoiser = instantiate_from_config(denoiser_config or DEFAULT_DENOISER)
         self.sampler = instantiate_from_config(sampler_config or default_sampler_config())
@@ -62,10 +64,12 @@ class DenoisingPipeline:
         return self
 
     @torch.no_grad()
-    def sample(self, cond: dict, uc: dict, randn: torch.Tensor, num_steps=None, use_last_frame: bool = False):
-        """diffusion.py:242-254: optional shared-noise mix `randn += level * repeat(concat[-1])`, then the sampler.
-        `randn` is the caller's CPU-generator draw moved to the device (the reference draws on CPU, :242)."""
+    def sample(self, cond: dict, uc: dict, randn: torch.Tensor, num_steps=None, share_noise: bool = True):
+        """diffusion.py:242-254: the shared-noise mix `randn += share_noise_level * repeat(concat[-1], t=num_frames)`,
+        applied like the reference whenever share_noise_level > 0 (it is 0.07 in inference_nuscenes.yaml; with
+        use_last_frame data concat[-1] is the conditioning frame's latent), then the sampler. `randn` is the caller's
+        CPU-generator draw moved to the device (the reference draws on CPU, :242). share_noise=False opts out."""
         x = randn.float()
-        if use_last_frame:
+        if share_noise and self.share_noise_level > 0.0:
             x = x + self.share_noise_level * cond["concat"][-1:].float().expand_as(x)
         return self.sampler(BoundDenoiser(self.denoiser, self.wrapper), x, cond, uc, num_steps=num_steps)

@@ -69,6 +69,16 @@ class _FlatParams(nn.Module):
     def reference_parameters(self) -> dict:
         return {k: getattr(self, a) for k, a in self._attr.items()}
 
+    def _apply(self, fn, recurse=True):
+        """.to() / .cuda() / .float() replace or rewrite the parameters: the packed operands are stale afterwards."""
+        r = super()._apply(fn, recurse)
+        self._pack_version += 1
+        return r
+
+    def mark_parameters_changed(self) -> None:
+        """Call after editing parameters in place (p.copy_(), p.mul_() ...): forces a repack on the next forward."""
+        self._pack_version += 1
+
     # --- state-dict plumbing with the reference's key names
     def _save_to_state_dict(self, destination, prefix, keep_vars):
         for k, a in self._attr.items():
@@ -98,15 +108,29 @@ class _FlatParams(nn.Module):
         self._pack_version += 1
 
 
-def _native_ops():
-    from ....ops import NativeOps
-    return NativeOps()
+PRECISIONS = ("bf16", "parity")
+
+
+def _resolve_precision(precision):
+    """Precision mode of the engine: "bf16" (default; bf16 tensor-core operands, fp32 accumulation / softmax / norms /
+    residual stream) or "parity" (split-bf16 operands = fp32-class products, fp32 attention: matches the reference's
+    fp32 math to rtol 1e-3 / atol 1e-4 at 3-4x the cost). Constructor kwarg `precision=`, else env PN_PRECISION."""
+    import os
+    p = precision if precision is not None else os.environ.get("PN_PRECISION", "bf16")
+    if p not in PRECISIONS:
+        raise ValueError(f"precision must be one of {PRECISIONS}, got {p!r}")
+    return p
+
+
+def _native_ops(precision: str = "bf16"):
+    from ....ops import NativeOps, ParityOps
+    return ParityOps() if precision == "parity" else NativeOps()
 
 
 class ControlNet3D(_FlatParams):
     """controlmodel.py:19-142. Encoder copy + BEV hint stem + 13 zero convolutions."""
 
-    def __init__(self, hint_channels, control_scales, dims=2, disable_temporal=False, *args, **kwargs):
+    def __init__(self, hint_channels, control_scales, dims=2, disable_temporal=False, *args, precision=None, **kwargs):
         if args:
             raise TypeError("ControlNet3D takes keyword arguments only (as instantiate_from_config passes them)")
         if dims != 2 or disable_temporal:
@@ -117,6 +141,7 @@ class ControlNet3D(_FlatParams):
         if hint_channels > 19:
             raise NotImplementedError("hint_channels > 19 (multi-map hints, controlmodel.py:108-117) is not supported")
         super().__init__(controlnet_param_spec(cfg))
+        self.precision = _resolve_precision(precision)
         self.cfg: NetConfig = cfg
         self.control_scales = control_scales
         self.hint_channels = hint_channels
@@ -128,7 +153,7 @@ class ControlNet3D(_FlatParams):
 
     def _standalone_engine(self) -> Engine:
         if self._engine is None:
-            self._engine = Engine(self.cfg, _native_ops())
+            self._engine = Engine(self.cfg, _native_ops(self.precision))
         if self._engine_version != self._pack_version:
             self._engine.pack(None, self.reference_parameters())
             self._engine_version = self._pack_version
@@ -162,11 +187,12 @@ class ControlNet3D(_FlatParams):
 class ControlledUNetModel3D(_FlatParams):
     """controlmodel.py:146-202. UNet whose decoder consumes the ControlNet residuals; owns `.controlnet`."""
 
-    def __init__(self, controlnet_config=None, only_add_on_center_frame=False, *args, **kwargs):
+    def __init__(self, controlnet_config=None, only_add_on_center_frame=False, *args, precision=None, **kwargs):
         if args:
             raise TypeError("ControlledUNetModel3D takes keyword arguments only")
         cfg = config_from_kwargs(dict(kwargs))
         super().__init__(unet_param_spec(cfg))
+        self.precision = _resolve_precision(precision)
         self.cfg: NetConfig = cfg
         self.num_frames = self.cfg.num_frames
         self.num_classes = None
@@ -174,7 +200,7 @@ class ControlledUNetModel3D(_FlatParams):
         self.in_channels = self.cfg.in_channels
         self.out_channels = self.cfg.out_channels
         self._engine: Engine | None = None
-        self._engine_version = (-1, -1)
+        self._engine_version = None
         if controlnet_config is not None:
             self.controlnet = instantiate_from_config(controlnet_config)
             cn = self.controlnet.cfg
@@ -183,12 +209,20 @@ class ControlledUNetModel3D(_FlatParams):
             self.cfg.hint_channels = cn.hint_channels
             self.cfg.control_scales = cn.control_scales
 
+    def set_precision(self, precision: str) -> None:
+        """Switch between "bf16" and "parity"; the engine (packed weights, caches) is rebuilt on the next call."""
+        self.precision = _resolve_precision(precision)
+        self._engine = None
+        self._engine_version = None
+        self._pack_version += 1           # wrappers key their caches / captured graph on the pack generation
+
     def engine(self) -> Engine:
-        """Lazily builds the engine and (re)packs bf16 operands whenever parameters changed."""
+        """Lazily builds the engine and (re)packs the MMA operands whenever parameters changed."""
         if self._engine is None:
-            self._engine = Engine(self.cfg, _native_ops())
+            self._engine = Engine(self.cfg, _native_ops(self.precision))
         cn = getattr(self, "controlnet", None)
-        ver = (self._pack_version, cn._pack_version if cn is not None else -1)
+        dev = getattr(self, next(iter(self._attr.values()))).device
+        ver = (self._pack_version, cn._pack_version if cn is not None else -1, str(dev))
         if self._engine_version != ver:
             self._engine.pack(self.reference_parameters(), cn.reference_parameters() if cn is not None else None)
             self._engine_version = ver

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
     assert set(_lib.SIGNATURES) == set(names)
-    assert lib.pn_abi_version() == 1
+    assert lib.pn_abi_version() == 2
 
 
 def test_struct_layout_matches_header_field_order():

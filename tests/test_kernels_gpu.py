@@ -200,7 +200,7 @@ def test_layout_and_small_ops(ops):
     cat = ops.concat_add(h, skip, ctrl)
     cat2 = ops.concat_add(h, skip, None)
     a = h.clone(); ops.add_(a, h)
-    cb = ops.cast_bf16(h)
+    cb = ops.cast_operand(h)
     torch.cuda.synchronize()
     assert torch.equal(up, ref.to(torch.bfloat16))
     assert torch.equal(cat, torch.cat([h, skip + ctrl], -1)) and torch.equal(cat2, torch.cat([h, skip], -1))

@@ -16,7 +16,7 @@ GOLDEN = Path(__file__).resolve().parent / "golden"
 def test_eps_port_matches_reference_golden(name):
     case = [c for c in Cs.GOLDEN_CASES if c.name == name][0]
     g = torch.load(GOLDEN / f"eps_{name}.pt")
-    assert g["meta"] == case.meta()
+    assert {"last_frame_concat": False, **g["meta"]} == case.meta()     # fixtures made before the field existed lack it
     x, t, c = Cs.make_inputs(case)
     eps = P.wrapper_forward(Cs.make_weights(case), case.net_config(), x, t, c)
     assert eps.shape == g["eps"].shape
@@ -64,3 +64,19 @@ def test_sampler_loop_matches_reference_golden():
     assert seen == g["timestep_indices"]
     rel = ((out - g["x_final"]).norm() / g["x_final"].norm()).item()
     assert rel < 1e-4, rel
+
+
+def test_sampler_port_follows_the_reference_25_step_trajectory():
+    """First 3 steps of the reference's 25-step loop on the head_dim-64 model with the use_last_frame shared-noise init
+    (diffusion.py:242-249): the oracle sampler port must land on the committed reference trajectory."""
+    from oracle import sampler_port as SP
+    from oracle.make_golden import sampler_inputs
+    case = Cs.SAMPLER_CASE
+    g = torch.load(GOLDEN / f"sampler_{case.name}_25.pt")
+    assert g["use_last_frame"] and g["timestep_indices"] == list(range(999, 0, -40))
+    x, c, uc = sampler_inputs(case, True)
+    x = x + c["concat"][-1].unsqueeze(0).expand_as(x) * g["share_noise_level"]
+    sd, cfg = Cs.make_weights(case), case.net_config()
+    out = SP.euler_edm_sample(lambda xi, ti, ci: P.wrapper_forward(sd, cfg, xi, ti, ci), x, c, uc, 25, g["scale"], max_steps=3)
+    ref = g["x_steps"][3]
+    assert ((out - ref).norm() / ref.norm()).item() < 1e-5

@@ -16,8 +16,20 @@ F32 = torch.float32
 
 
 class TorchRefOps:
+    """fp32 everywhere: operands are plain fp32 tensors, weights stay fp32."""
+    operand_mult = 1
+    qkv_dtype = F32
+    act_dtype = F32
+    fused_operand_emit = False
+
     def __init__(self):
         self.launches = 0
+
+    def pack_matrix(self, w, taps=1):
+        return w.detach().to(F32).contiguous()
+
+    def pack_small(self, w):
+        return w.detach().to(F32).contiguous()
 
     def gemm(self, a, w, *, bias=None, rowvec=None, rows_per_group=0, n_groups=0, residual=None, residual2=None,
              geglu=False, out_dtype=F32, taps=(1, 1), out=None):
@@ -56,7 +68,7 @@ class TorchRefOps:
             return out.reshape(*lead, y.shape[1])
         return y.reshape(*lead, y.shape[1])
 
-    def groupnorm(self, x, gamma, beta, eps, silu, want_raw=False):
+    def groupnorm(self, x, gamma, beta, eps, silu, want_raw=False, out_f32=False):
         Fr, C = x.shape[0], x.shape[-1]
         z = x.reshape(Fr, -1, C).permute(0, 2, 1)
         y = F.group_norm(z, 32, gamma, beta, eps)
@@ -137,8 +149,8 @@ class TorchRefOps:
     def add_(self, x, y):
         return x.add_(y)
 
-    def cast_bf16(self, x):
-        return x.to(torch.bfloat16)
+    def cast_operand(self, x):
+        return x
 
     def nchw_to_nhwc(self, x, out=None, ch_off=0):
         y = x.permute(0, 2, 3, 1)
@@ -173,3 +185,58 @@ class TorchRefOps:
 
     def scale_dup(self, x, s, copies):
         return torch.cat([x * s] * copies)
+
+
+def _enc(x):
+    """operand.cuh PN_OP_SPLIT3: fp32 [..., C] -> bf16 [..., 3C] = [hi | lo | hi]."""
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return torch.cat([hi, lo, hi], dim=-1)
+
+
+class TorchSplitOps(TorchRefOps):
+    """CPU emulation of panacea_b200.ops.ParityOps: producers store split-bf16 operands [hi | lo | hi], weights are
+    packed [W_hi | W_hi | W_lo] by the product's own split3(), and the GEMM multiplies the bf16 VALUES exactly as the
+    tensor core does (bf16 x bf16 products are exact in fp32). Checks the engine's parity-mode packing/orchestration and
+    the precision claim of the encoding without a GPU."""
+    operand_mult = 3
+
+    def pack_matrix(self, w, taps=1):
+        from panacea_b200.ops import split3
+        return split3(w, taps)
+
+    def gemm(self, a, w, *, geglu=False, out_dtype=F32, **kw):
+        y = super().gemm(a, w, geglu=geglu, out_dtype=F32, **kw)
+        return _enc(y) if geglu else y
+
+    def groupnorm(self, x, gamma, beta, eps, silu, want_raw=False, out_f32=False):
+        r = super().groupnorm(x, gamma, beta, eps, silu, want_raw)
+        if out_f32:
+            return r
+        return (_enc(r[0]), _enc(r[1])) if want_raw else _enc(r)
+
+    def groupnorm_pixel(self, *a, **k):
+        return _enc(super().groupnorm_pixel(*a, **k))
+
+    def layernorm(self, *a, **k):
+        return _enc(super().layernorm(*a, **k))
+
+    def attention_view(self, *a, **k):
+        return _enc(super().attention_view(*a, **k))
+
+    def attention_text(self, *a, **k):
+        return _enc(super().attention_text(*a, **k))
+
+    def attention_temporal(self, *a, **k):
+        return _enc(super().attention_temporal(*a, **k))
+
+    def im2col_s2(self, x):
+        cols, geo = super().im2col_s2(x)
+        C = x.shape[-1]
+        return _enc(cols.reshape(cols.shape[0], 9, C)).reshape(cols.shape[0], 27 * C), geo
+
+    def upsample2x(self, x):
+        return _enc(super().upsample2x(x))
+
+    def cast_operand(self, x):
+        return _enc(x)
