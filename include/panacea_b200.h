@@ -61,7 +61,7 @@ typedef struct pn_gemm_args {
   void* out;              /* fp32 or bf16 [NB*H*W, ldo] */
   const float* bias;      /* [N] or NULL */
   const float* rowvec;    /* [n_groups, N] or NULL */
-  const float* residual;  /* fp32 [NB*H*W, ldr] or NULL (may alias out when both fp32) */
+  const void* residual;   /* fp32 (or bf16 when residual_bf16) [NB*H*W, ldr] or NULL (may alias out when same dtype) */
   const float* residual2; /* second fp32 addend [NB*H*W, ldr2] or NULL (fp32 output only) */
   int64_t NB, H, W, C;
   int64_t a_stride_w, a_stride_h, a_stride_n; /* elements */
@@ -72,6 +72,7 @@ typedef struct pn_gemm_args {
   int32_t rows_per_group, n_groups;
   int32_t out_bf16;
   int32_t geglu;
+  int32_t residual_bf16;  /* the residual is bf16 (bf16 output only): the transformer blocks' bf16 token stream */
 } pn_gemm_args;
 
 int pn_gemm(const pn_gemm_args* args, void* stream);
@@ -136,9 +137,10 @@ int pn_groupnorm_silu(const float* x, const float* gamma, const float* beta, voi
 int pn_groupnorm_pixel_silu(const float* x, const float* gamma, const float* beta, void* y, int64_t batch,
                             int64_t frames_per_seq, int64_t pixels, int64_t channels, float eps, int act_silu,
                             int operand_mode, void* stream);
-/* nn.LayerNorm(C) per token, eps 1e-5 (attention.py:699-701). */
-int pn_layernorm(const float* x, const float* gamma, const float* beta, void* y, int64_t rows, int64_t channels,
-                 float eps, int operand_mode, void* stream);
+/* nn.LayerNorm(C) per token, eps 1e-5 (attention.py:699-701). x: fp32, or bf16 (x_is_bf16: the bf16 token stream the
+ * fast path keeps inside a transformer block). */
+int pn_layernorm(const void* x, int x_is_bf16, const float* gamma, const float* beta, void* y, int64_t rows,
+                 int64_t channels, float eps, int operand_mode, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Convolutions that cannot feed a 64-wide UMMA K block, layout and sampler helpers

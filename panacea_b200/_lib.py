@@ -27,7 +27,7 @@ class GemmArgs(C.Structure):
         ("ldo", C.c_int64), ("ldr", C.c_int64), ("ldr2", C.c_int64), ("rowvec_ld", C.c_int64),
         ("N", C.c_int32), ("taps_h", C.c_int32), ("taps_w", C.c_int32),
         ("rows_per_group", C.c_int32), ("n_groups", C.c_int32),
-        ("out_bf16", C.c_int32), ("geglu", C.c_int32),
+        ("out_bf16", C.c_int32), ("geglu", C.c_int32), ("residual_bf16", C.c_int32),
     ]
 
 
@@ -58,7 +58,7 @@ SIGNATURES: dict[str, tuple] = {
     "pn_groupnorm_workspace_floats": (_i64, [_i64, _i64, _i64]),
     "pn_groupnorm_silu": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _f32, C.c_int, C.c_int, _vp]),
     "pn_groupnorm_pixel_silu": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _f32, C.c_int, C.c_int, _vp]),
-    "pn_layernorm": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _f32, C.c_int, _vp]),
+    "pn_layernorm": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _i64, _i64, _f32, C.c_int, _vp]),
     "pn_conv3x3_direct": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64,
                                     C.c_int, C.c_int, _vp]),
     "pn_im2col3x3_s2": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, C.c_int, _vp]),

@@ -55,6 +55,7 @@ struct GemmParams {
   long long ldo, ldr, ldr2, ldv;
   int rows_per_group, n_groups;
   int out_bf16;
+  int res_bf16;                // the residual is bf16 (bf16 token stream of the transformer blocks), bf16 output only
   int geglu;
   int bstat;                   // weight-stationary schedule (K = 5 k-blocks, taps = 1): see gemm_tc_kernel
 };
@@ -555,9 +556,18 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
             uint8_t* rowp = staging + c * S::RCHUNK_BYTES + r * 64;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              *reinterpret_cast<uint4*>(rowp + ((j ^ ((r >> 1) & 3)) << 4)) =
-                  make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                             pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+              uint4* q = reinterpret_cast<uint4*>(rowp + ((j ^ ((r >> 1) & 3)) << 4));
+              if (p.has_res) {     // bf16 residual tile (TMA-loaded into this chunk): add in fp32, round once
+                const uint4 a = *q;
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 t = __bfloat1622float2(h[e]);
+                  f[8 * j + 2 * e] += t.x; f[8 * j + 2 * e + 1] += t.y;
+                }
+              }
+              *q = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                              pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
             }
           } else {
             uint8_t* rowp = staging + c * S::RCHUNK_BYTES + r * 128;
@@ -740,9 +750,19 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
                 const int sw = ch ^ ((rr >> 1) & 3);
                 uint4 val = *reinterpret_cast<const uint4*>(my_stage + rr * 64 + sw * 16);
                 if (p.residual != nullptr) {
-                  const float* rp = p.residual + (long long)grow * p.ldr + n0 + ch * 8;
-                  const float4 r0 = *reinterpret_cast<const float4*>(rp);
-                  const float4 r1 = *reinterpret_cast<const float4*>(rp + 4);
+                  float4 r0, r1;
+                  if (p.res_bf16) {
+                    const uint4 rb = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) +
+                                                                     (long long)grow * p.ldr + n0 + ch * 8);
+                    const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&rb);
+                    const float2 t0 = __bfloat1622float2(hb[0]), t1 = __bfloat1622float2(hb[1]);
+                    const float2 t2 = __bfloat1622float2(hb[2]), t3 = __bfloat1622float2(hb[3]);
+                    r0 = make_float4(t0.x, t0.y, t1.x, t1.y); r1 = make_float4(t2.x, t2.y, t3.x, t3.y);
+                  } else {
+                    const float* rp = p.residual + (long long)grow * p.ldr + n0 + ch * 8;
+                    r0 = *reinterpret_cast<const float4*>(rp);
+                    r1 = *reinterpret_cast<const float4*>(rp + 4);
+                  }
                   __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&val);
                   float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
                   float2 c2 = __bfloat1622float2(h[2]), d = __bfloat1622float2(h[3]);
@@ -940,6 +960,8 @@ extern "C" int pn_gemm(const pn_gemm_args* a, void* stream_v) {
   PN_REQUIRE(a->ldo >= n_out && a->ldo % 8 == 0, "pn_gemm: ldo=%lld too small or misaligned", (long long)a->ldo);
   if (a->geglu) PN_REQUIRE(a->out_bf16 && a->residual == nullptr && a->N % 32 == 0, "pn_gemm: GEGLU needs bf16 out, no residual, N%%32==0");
   if (a->residual) PN_REQUIRE(a->ldr >= a->N && a->ldr % 4 == 0, "pn_gemm: bad ldr");
+  if (a->residual_bf16) PN_REQUIRE(a->residual && a->out_bf16 && !a->geglu && a->residual2 == nullptr && a->ldr % 8 == 0,
+                                   "pn_gemm: a bf16 residual needs bf16 output, no GEGLU, no second residual, ldr%%8==0");
   if (a->residual2) PN_REQUIRE(!a->out_bf16 && !a->geglu && a->ldr2 >= a->N && a->ldr2 % 4 == 0, "pn_gemm: residual2 needs fp32 out and a valid ldr2");
   if (a->rowvec) PN_REQUIRE(a->rows_per_group > 0 && a->n_groups > 0, "pn_gemm: rowvec needs rows_per_group/n_groups");
 
@@ -962,14 +984,14 @@ extern "C" int pn_gemm(const pn_gemm_args* a, void* stream_v) {
   p.taps_h = a->taps_h; p.taps_w = a->taps_w;
   p.pad_h = a->taps_h / 2; p.pad_w = a->taps_w / 2;
   p.N = a->N;
-  p.out = a->out; p.bias = a->bias; p.rowvec = a->rowvec; p.residual = a->residual;
+  p.out = a->out; p.bias = a->bias; p.rowvec = a->rowvec; p.residual = reinterpret_cast<const float*>(a->residual);
   p.residual2 = a->residual2;
   p.debug = gemm_debug_mode();
   p.ldo = a->ldo; p.ldr = a->ldr; p.ldr2 = a->ldr2;
   p.ldv = a->rowvec_ld > 0 ? a->rowvec_ld : a->N;
   p.rows_per_group = a->rows_per_group > 0 ? a->rows_per_group : 1;
   p.n_groups = a->n_groups > 0 ? a->n_groups : 1;
-  p.out_bf16 = a->out_bf16; p.geglu = a->geglu;
+  p.out_bf16 = a->out_bf16; p.geglu = a->geglu; p.res_bf16 = a->residual_bf16;
 
   // Tile selection. Big problems run on CTA pairs (cta_group::2, 256 x BN tiles: the weight tile is fetched once per
   // pair, which is what lifts the L2->SM-bound K loop); small ones keep single-CTA 128 x BN tiles for parallelism.
@@ -1000,7 +1022,7 @@ extern "C" int pn_gemm(const pn_gemm_args* a, void* stream_v) {
   // Streaming epilogue (MODE 4): fp32 output whose tile rows are consecutive output rows, short K loop (HBM-bound).
   const long long k_total = (long long)a->taps_h * a->taps_w * a->C;
   const bool rows_contig = (tw == 128 && th == 1 && tn == 1) && ((H == 1 && NB == 1) || (W % 128 == 0));
-  const bool stream_bf16 = a->out_bf16 && !a->geglu && a->residual == nullptr && a->ldo % 8 == 0;
+  const bool stream_bf16 = a->out_bf16 && !a->geglu && (a->residual == nullptr || a->residual_bf16) && a->ldo % 8 == 0;
   const bool stream_f32 = !a->out_bf16 && !a->geglu && a->ldo % 4 == 0 && (a->residual == nullptr || a->ldr % 4 == 0);
   // measured on B200: the fp32 variant wins up to K = 1920 (ff2 at level 0, temporal conv), the bf16 variant up to K = 640
   const long long kmax = stream_bf16 ? (gemm_stream_kmax() < 640 ? gemm_stream_kmax() : 640) : gemm_stream_kmax();
@@ -1022,7 +1044,14 @@ extern "C" int pn_gemm(const pn_gemm_args* a, void* stream_v) {
     if (rc2 != PN_OK) return rc2;
     p.has_res = a->residual != nullptr ? 1 : 0;
     if (p.has_res) {
-      rc2 = cached_tmap_f32_2d(&p.mapRes, a->residual, (uint64_t)a->N, rows_total, (uint64_t)a->ldr, 128u);
+      if (stream_bf16) {
+        const uint64_t dimsR[2] = {(uint64_t)a->N, rows_total};
+        const uint64_t strR[1] = {(uint64_t)a->ldr};
+        const uint32_t boxR[2] = {32u, 128u};
+        rc2 = cached_tmap_bf16(&p.mapRes, a->residual, 2, dimsR, strR, boxR, 64);
+      } else {
+        rc2 = cached_tmap_f32_2d(&p.mapRes, a->residual, (uint64_t)a->N, rows_total, (uint64_t)a->ldr, 128u);
+      }
       if (rc2 != PN_OK) return rc2;
     }
   }

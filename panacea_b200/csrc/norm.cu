@@ -247,14 +247,23 @@ __global__ void __launch_bounds__(512) gn_pixel_kernel(const float* __restrict__
 
 // ---------------------------------------------------------------- LayerNorm per token -> bf16
 // one warp per row; the row (C <= 2048 floats) lives in registers between the two passes.
-template <int MAXV, int OP>
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+__device__ __forceinline__ float4 ln_load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ln_load4(const __nv_bfloat16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// TIn: fp32 residual stream, or the bf16 token stream of the transformer blocks (fast path)
+template <int MAXV, int OP, typename TIn>
+__global__ void __launch_bounds__(256) layernorm_kernel(const TIn* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, void* __restrict__ y,
                                                         long long rows, int C, float eps) {
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
-  const float4* xr = reinterpret_cast<const float4*>(x + row * C);
+  const TIn* xr = x + row * C;
   const int n4 = C / 4;
   float4 v[MAXV];
   float s = 0.f;
@@ -262,7 +271,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   for (int i = 0; i < MAXV; ++i) {
     const int j = lane + i * 32;
     if (j < n4) {
-      v[i] = xr[j];
+      v[i] = ln_load4(xr + 4 * j);
       s += v[i].x + v[i].y + v[i].z + v[i].w;
     }
   }
@@ -413,7 +422,7 @@ extern "C" int pn_groupnorm_pixel_silu(const float* x, const float* gamma, const
   return PN_OK;
 }
 
-extern "C" int pn_layernorm(const float* x, const float* gamma, const float* beta, void* y, int64_t rows,
+extern "C" int pn_layernorm(const void* x, int x_is_bf16, const float* gamma, const float* beta, void* y, int64_t rows,
                             int64_t channels, float eps, int operand_mode, void* stream_v) {
   PN_REQUIRE(x && gamma && beta && y, "pn_layernorm: null pointer");
   PN_REQUIRE(channels % 4 == 0 && channels <= 2048 && channels > 0, "pn_layernorm: C=%lld unsupported", (long long)channels);
@@ -422,9 +431,19 @@ extern "C" int pn_layernorm(const float* x, const float* gamma, const float* bet
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
   const long long blocks = (rows * 32 + 255) / 256;
   const int C = (int)channels;
-  if (C <= 512) PN_DISPATCH_OP(operand_mode, (layernorm_kernel<4, OP><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, beta, y, rows, C, eps)));
-  else if (C <= 1024) PN_DISPATCH_OP(operand_mode, (layernorm_kernel<8, OP><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, beta, y, rows, C, eps)));
-  else PN_DISPATCH_OP(operand_mode, (layernorm_kernel<16, OP><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, beta, y, rows, C, eps)));
+#define PN_LN(MAXV)                                                                                                          \
+  do {                                                                                                                      \
+    if (x_is_bf16)                                                                                                          \
+      PN_DISPATCH_OP(operand_mode, (layernorm_kernel<MAXV, OP, __nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(             \
+                                       reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta, y, rows, C, eps)));           \
+    else                                                                                                                    \
+      PN_DISPATCH_OP(operand_mode, (layernorm_kernel<MAXV, OP, float><<<(unsigned)blocks, 256, 0, st>>>(                     \
+                                       reinterpret_cast<const float*>(x), gamma, beta, y, rows, C, eps)));                   \
+  } while (0)
+  if (C <= 512) PN_LN(4);
+  else if (C <= 1024) PN_LN(8);
+  else PN_LN(16);
+#undef PN_LN
   PN_CHECK_CUDA(cudaGetLastError());
   return PN_OK;
 }

@@ -256,18 +256,19 @@ class Engine:
         else:
             V = self.cfg.num_views
             o = ops.attention_view(qkv.view(Fr, H, V, Wd // V, 3 * C), heads, mode == "cross", CROSS_VIEW_NEIGHBOURS)
-        y = ops.gemm(o.view(-1, o.shape[-1]), W[t + ".attn1.o.w"], bias=W[t + ".attn1.o.b"], residual=y, out=y)
+        tok = y.dtype                                    # token stream: bf16 in the fast path (ops.token_dtype), fp32 otherwise
+        y = ops.gemm(o.view(-1, o.shape[-1]), W[t + ".attn1.o.w"], bias=W[t + ".attn1.o.b"], residual=y, out=y, out_dtype=tok)
         n2 = ops.layernorm(y, W[t + ".norm2.g"], W[t + ".norm2.b"])
         q = ops.gemm(n2, W[t + ".q2.w"], out_dtype=dt)
         o = ops.attention_text(q.view(b, T * H * Wd, C), kv, heads)
-        y = ops.gemm(o.view(-1, o.shape[-1]), W[t + ".attn2.o.w"], bias=W[t + ".attn2.o.b"], residual=y, out=y)
+        y = ops.gemm(o.view(-1, o.shape[-1]), W[t + ".attn2.o.w"], bias=W[t + ".attn2.o.b"], residual=y, out=y, out_dtype=tok)
         n3 = ops.layernorm(y, W[t + ".norm3.g"], W[t + ".norm3.b"])
         ff = ops.gemm(n3, W[t + ".ff1.w"], bias=W[t + ".ff1.b"], geglu=True, out_dtype=ops.act_dtype)
         # the block's output is only ever consumed as the bf16 operand of proj_out: emit it in that form directly
         # (saves the fp32 write, the cast kernel's fp32 read and one launch per transformer block)
         if ops.fused_operand_emit:
             return ops.gemm(ff, W[t + ".ff2.w"], bias=W[t + ".ff2.b"], residual=y, out_dtype=torch.bfloat16)
-        return ops.gemm(ff, W[t + ".ff2.w"], bias=W[t + ".ff2.b"], residual=y, out=y)
+        return ops.gemm(ff, W[t + ".ff2.w"], bias=W[t + ".ff2.b"], residual=y, out=y, out_dtype=tok)
 
     def _stt(self, W, st: Stage, x):
         """SpatialTemporalTransformer.forward (attention.py:1064-1134): intra-view, cross-view, temporal."""
@@ -280,9 +281,10 @@ class Engine:
             if mode == "temporal":
                 pe = self._pos_table(T, C, x.device)
                 y = ops.gemm(a.view(-1, a.shape[-1]), W[f"{k}.proj_in{br}.w"], bias=W[f"{k}.proj_in{br}.b"], rowvec=pe,
-                             rows_per_group=H * Wd, n_groups=T)
+                             rows_per_group=H * Wd, n_groups=T, out_dtype=ops.token_dtype)
             else:
-                y = ops.gemm(a.view(-1, a.shape[-1]), W[f"{k}.proj_in{br}.w"], bias=W[f"{k}.proj_in{br}.b"])
+                y = ops.gemm(a.view(-1, a.shape[-1]), W[f"{k}.proj_in{br}.w"], bias=W[f"{k}.proj_in{br}.b"],
+                             out_dtype=ops.token_dtype)
             t = f"{k}.transformer_blocks{br}.0"
             y = self._transformer(W, t, y, st.heads, mode, geom, self.cond["kv"][(W.tag, t)])
             yb = self._to_operand(y) if y.dtype == F32 else y

@@ -60,11 +60,15 @@ class NativeOps:
     qkv_dtype = BF16          # dtype of attention inputs
     act_dtype = BF16          # dtype of intermediates consumed by CUDA-core kernels (hint stem, GEGLU output, head input)
     fused_operand_emit = True # a GEMM epilogue may store the next GEMM's operand directly (out_dtype=bf16)
+    token_dtype = BF16        # token stream inside a transformer block (proj_in .. proj_out): 3 residual adds per block
 
     def __init__(self):
+        import os
         self.lib = _lib.load()
         self.launches = 0
         self._freqs = {}
+        if os.environ.get("PN_TOKEN_F32") == "1" and self.operand_mode == OP_BF16:      # A/B measurement of the bf16 token stream
+            self.token_dtype = F32
 
     def pack_matrix(self, w: torch.Tensor, taps: int = 1) -> torch.Tensor:
         """fp32 weight [N, taps*C] -> the B operand pn_gemm reads in this op set's precision mode."""
@@ -140,9 +144,11 @@ class NativeOps:
             _req(rows_per_group > 0 and n_groups > 0 and rowvec.shape[0] == n_groups, "gemm: rowvec groups")
             args.rowvec_ld = rowvec.stride(0)
         if residual is not None:
-            _req(residual.dtype == F32 and residual.stride(-1) == 1, "gemm: residual must be fp32")
+            _req(residual.stride(-1) == 1 and (residual.dtype == F32 or (residual.dtype == BF16 and out_dtype == BF16)),
+                 "gemm: residual must be fp32 (or bf16 with a bf16 output)")
             r2 = residual.reshape(rows, -1) if residual.is_contiguous() else residual
             args.ldr = r2.stride(0)
+            args.residual_bf16 = int(residual.dtype == BF16)
         if residual2 is not None:
             _req(residual2.dtype == F32 and residual2.is_contiguous() and out_dtype == F32, "gemm: residual2 must be fp32")
             args.residual2 = residual2.data_ptr()
@@ -186,12 +192,12 @@ class NativeOps:
         return y
 
     def layernorm(self, x, gamma, beta, eps=1e-5):
-        _req(x.is_cuda and x.dtype == F32 and x.is_contiguous(), "layernorm: x must be contiguous CUDA fp32")
+        _req(x.is_cuda and x.dtype in (F32, BF16) and x.is_contiguous(), "layernorm: x must be contiguous CUDA fp32 / bf16")
         Cc = x.shape[-1]
         rows = x.numel() // Cc
         y = self._operand_empty(x.shape, x.device)
-        _lib.check(self.lib.pn_layernorm(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), rows, Cc, float(eps), self.operand_mode,
-                                         _stream()), "pn_layernorm")
+        _lib.check(self.lib.pn_layernorm(_ptr(x), int(x.dtype == BF16), _ptr(gamma), _ptr(beta), _ptr(y), rows, Cc, float(eps),
+                                         self.operand_mode, _stream()), "pn_layernorm")
         self.launches += 1
         return y
 
@@ -392,6 +398,7 @@ class ParityOps(NativeOps):
     qkv_dtype = F32
     act_dtype = F32
     fused_operand_emit = False
+    token_dtype = F32
 
     def pack_matrix(self, w, taps=1):
         return split3(w, taps)

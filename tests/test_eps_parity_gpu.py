@@ -24,7 +24,7 @@ GOLDEN = Path(__file__).resolve().parent / "golden"
 BOUNDS = {  # mode -> (rel-L2, max-abs / rms, min fraction inside rtol 1e-3 / atol 1e-4)
     "bf16": (8.5e-3, 0.04, 0.0),
     "parity": (1e-4, 1e-3, 0.999),
-    "bf16_loop": (3e-2, 0.2, 0.0),        # 25/50 chained bf16 evaluations: the per-step error compounds (provisional)
+    "bf16_loop": (6.5e-3, 0.03, 0.0),     # 25/50 chained bf16 evaluations (measured 4.9e-3 / 3.4e-3, max-abs 2.1 % of rms)
 }
 
 
@@ -237,9 +237,14 @@ def test_sampler_loop_vs_reference_golden(steps, precision):
         curve.append(float(d.norm() / ref_steps[i].double().norm()))
     d = (out - g["x_final"]).double()
     curve.append(float(d.norm() / g["x_final"].double().norm()))
-    rec = _report(f"sampler{steps}{'_last_frame' if g['use_last_frame'] else ''}:x_final_vs_reference", out, g["x_final"],
+    # The seeded random-weight network is no denoiser: the latent stays at the sigma_0 scale (rms 16.3) instead of ending
+    # at unit scale like a trained model's. rtol/atol are therefore applied to the latent normalised by the reference's
+    # rms (atol 1e-4 is a unit-scale bound); the raw-scale pass rate is recorded next to it.
+    rms = g["x_final"].double().pow(2).mean().sqrt().item()
+    raw_frac = (d.abs() <= 1e-4 + 1e-3 * g["x_final"].double().abs()).double().mean().item()
+    rec = _report(f"sampler{steps}{'_last_frame' if g['use_last_frame'] else ''}:x_final_vs_reference", out / rms, g["x_final"] / rms,
                   "parity" if precision == "parity" else "bf16_loop",
-                  {"rel_l2_after_step": [round(v, 7) for v in curve]})
+                  {"rel_l2_after_step": [round(v, 7) for v in curve], "latent_rms": rms, "frac_within_tol_at_raw_scale": raw_frac})
     assert rec is not None
 
 

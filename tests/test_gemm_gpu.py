@@ -63,6 +63,24 @@ def test_gemm_bf16_out_and_rowvec(ops):
     _check(out, ref, tol=1e-2, name="bf16 out + rowvec")
 
 
+@pytest.mark.parametrize("M,N,K", [(3000, 320, 320), (2048, 640, 640), (1500, 1280, 1280), (172032 // 4, 320, 1280), (130, 320, 320)])
+def test_gemm_bf16_token_stream_residual(ops, M, N, K):
+    """bf16 output with a bf16 residual updated in place (the transformer blocks' token stream): streaming epilogue
+    (K <= 640, TMA-loaded residual tile) and the generic bf16 epilogue (larger K)."""
+    a = _rand((M, K), 13); w = _rand((N, K), 14, K ** -0.5)
+    bias = _rand((N,), 15, dtype=torch.float32)
+    y = _rand((M, N), 16)
+    ref = a.float() @ w.float().t() + bias + y.float()
+    out = ops.gemm(a, w, bias=bias, residual=y, out=y, out_dtype=torch.bfloat16)
+    torch.cuda.synchronize()
+    assert out.data_ptr() == y.data_ptr()
+    _check(out, ref, tol=1e-2, name="bf16 residual in place")
+    y2 = _rand((M, N), 17)
+    out2 = ops.gemm(a, w, residual=y2, out_dtype=torch.bfloat16)        # not in place
+    torch.cuda.synchronize()
+    _check(out2, a.float() @ w.float().t() + y2.float(), tol=1e-2, name="bf16 residual")
+
+
 def test_gemm_geglu(ops):
     M, C = 1500, 320
     a = _rand((M, C), 10)

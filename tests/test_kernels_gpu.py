@@ -67,6 +67,10 @@ def test_layernorm(ops, rows, C):
     y = ops.layernorm(x, g, b, 1e-5)
     torch.cuda.synchronize()
     _close(y, F.layer_norm(x, (C,), g, b, 1e-5), 1e-2, "layernorm")
+    xb = x.to(torch.bfloat16)                           # bf16 token stream input
+    yb = ops.layernorm(xb, g, b, 1e-5)
+    torch.cuda.synchronize()
+    _close(yb, F.layer_norm(xb.float(), (C,), g, b, 1e-5), 1e-2, "layernorm bf16 in")
 
 
 # ------------------------------------------------------------------------------------------------ attention

@@ -21,6 +21,7 @@ class TorchRefOps:
     qkv_dtype = F32
     act_dtype = F32
     fused_operand_emit = False
+    token_dtype = F32
 
     def __init__(self):
         self.launches = 0
