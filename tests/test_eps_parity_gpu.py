@@ -8,8 +8,8 @@ Two precision modes, two bars:
    full-size model at the benchmarked shape [16, 8, 32, 336] (T = 8, CFG b = 2);
  * "bf16" (the benchmarked fast path: bf16 operands, fp32 accumulation / softmax / norm statistics / residual stream):
    the reference's own network under bf16 autocast deviates from its fp32 output by rel-L2 1.7e-2 (BASELINE.md section 2);
-   the bound asserted here is ~1.2x what this path measures (rel-L2 <= 8.5e-3, max-abs <= 4 % of the output rms), so a
-   regression shows, and the measured rtol/atol pass rate is recorded in gpurun_out/parity.jsonl.
+   the bound asserted here is ~1.2x what this path measures (rel-L2 <= 9.5e-3, max-abs <= 4.6 % of the output rms; measured
+   6.9e-3 .. 7.9e-3 and 2.8 .. 3.8 % with the bf16 token stream inside the transformer blocks), so a regression shows, and the measured rtol/atol pass rate is recorded in gpurun_out/parity.jsonl.
 """
 import json
 import os
@@ -22,9 +22,9 @@ pytestmark = pytest.mark.gpu
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
 BOUNDS = {  # mode -> (rel-L2, max-abs / rms, min fraction inside rtol 1e-3 / atol 1e-4)
-    "bf16": (8.5e-3, 0.04, 0.0),
+    "bf16": (9.5e-3, 0.046, 0.0),
     "parity": (1e-4, 1e-3, 0.999),
-    "bf16_loop": (6.5e-3, 0.03, 0.0),     # 25/50 chained bf16 evaluations (measured 4.9e-3 / 3.4e-3, max-abs 2.1 % of rms)
+    "bf16_loop": (7.5e-3, 0.033, 0.0),    # 25/50 chained bf16 evaluations (measured 6.1e-3 / 4.2e-3, max-abs 2.7 % of rms)
 }
 
 
@@ -185,7 +185,7 @@ def test_two_conditionings_back_to_back_are_not_confused():
         eps = w(x.cuda(), t.cuda(), cg).cpu()
         ref = P.wrapper_forward(sd, case.net_config(), x, t, c)
         rel = ((eps - ref).norm() / ref.norm()).item()
-        assert rel < 8.5e-3, (seed, rel)
+        assert rel < 9.5e-3, (seed, rel)
         outs.append(eps)
         n0 = len(calls)
         cg2 = {k: v.clone() for k, v in cg.items()}       # equal content, new tensors: fingerprint hit, no re-preparation
