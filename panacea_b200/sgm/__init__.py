@@ -15,7 +15,8 @@ _MIRRORED = (
     "sgm.modules.diffusionmodules.denoiser", "sgm.modules.diffusionmodules.denoiser_scaling",
     "sgm.modules.diffusionmodules.denoiser_weighting", "sgm.modules.diffusionmodules.discretizer",
     "sgm.modules.diffusionmodules.guiders", "sgm.modules.diffusionmodules.sampling",
-    "sgm.modules.diffusionmodules.sampling_utils",
+    "sgm.modules.diffusionmodules.sampling_utils", "sgm.modules.encoders", "sgm.modules.encoders.modules",
+    "sgm.models", "sgm.models.autoencoder", "sgm.models.diffusion",
 )
 
 
