@@ -183,6 +183,10 @@ int pn_linear_small(const float* x, const void* W, int w_is_f32, const float* bi
  * x is updated in place; x_in_next (optional, 2n elements) receives x_new * c_in_next duplicated. */
 int pn_cfg_euler_step(float* x, const float* net2, float* x_in_next, int64_t n, float sigma, float sigma_q,
                       float sigma_next, float cfg_scale, float c_in_next, int net_is_denoised, void* stream);
+/* out[r, :] = softmax(scale * in[r, :]), fp32 scores -> bf16 probabilities. With two pn_gemm calls around it this is the
+ * single-head attention of the VAE mid block (reference sgm/modules/diffusionmodules/model.py:374-414, head_dim = C). */
+int pn_softmax_rows(const float* in, void* out_bf16, int64_t rows, int64_t N, int64_t ld_in, int64_t ld_out, float scale,
+                    void* stream);
 /* Content fingerprint of a device buffer (two order-independent 64-bit sums over its 32-bit words) -> out2[2] on the
  * device. The wrapper keys its step-invariant conditioning cache (BEV hint stem, text K/V; wrappers.py:37-70 recomputes
  * them every step) on the CONTENT of c["cond_feat"] / c["crossattn"]: addresses are recycled by the allocator. */

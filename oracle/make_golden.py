@@ -97,6 +97,51 @@ def golden_sampler(case: Cs.EpsCase, num_steps: int = 10, scale: float = 5.0, us
     return res
 
 
+VAE_DDCONFIG = dict(double_z=True, z_channels=4, resolution=64, in_channels=3, out_ch=3, ch=64, ch_mult=[1, 2, 2], num_res_blocks=1,
+                    attn_resolutions=[], dropout=0.0)
+
+
+def vae_decoder_weights(spec: dict, seed: int = 7) -> dict:
+    """Seeded non-degenerate decoder weights keyed like the reference's AutoencoderKL state dict."""
+    import math
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    sd = {}
+    for k in sorted(spec):
+        shape = tuple(spec[k])
+        if k.endswith(".bias"):
+            sd[k] = 0.05 * torch.randn(shape, generator=g)
+        elif len(shape) == 1:
+            sd[k] = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        else:
+            sd[k] = torch.randn(shape, generator=g) / math.sqrt(math.prod(shape[1:]))
+    return sd
+
+
+def vae_decoder_input(seed: int = 8):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return torch.randn(2, 4, 8, 48, generator=g)           # 2 frames, latent 8 x (6 views x 8)
+
+
+@torch.no_grad()
+def golden_vae_decode() -> dict:
+    """Reference `AutoencoderKL.decode` = Decoder(post_quant_conv(z)) (autoencoder.py:362-365; model.py:882-1030) on a
+    shrunk ddconfig with seeded weights."""
+    R.import_reference()
+    import contextlib, io
+    from sgm.modules.diffusionmodules import model as M
+    from panacea_b200.vae import decoder_param_spec
+    spec = decoder_param_spec(VAE_DDCONFIG, 4)
+    sd = vae_decoder_weights(spec)
+    with contextlib.redirect_stdout(io.StringIO()):
+        dec = M.Decoder(**VAE_DDCONFIG).eval()
+    pq = torch.nn.Conv2d(4, 4, 1)
+    missing = dec.load_state_dict({k[len("decoder."):]: v for k, v in sd.items() if k.startswith("decoder.")}, strict=True)
+    pq.load_state_dict({"weight": sd["post_quant_conv.weight"], "bias": sd["post_quant_conv.bias"]})
+    z = vae_decoder_input()
+    out = dec(pq(z))
+    return {"ddconfig": VAE_DDCONFIG, "image": out.contiguous(), "keys": sorted(spec)}
+
+
 def sampler_inputs(case: Cs.EpsCase, use_last_frame: bool = False):
     """One sequence (case.b is ignored: the sampler doubles the batch itself): init noise, c and uc dicts."""
     g = torch.Generator(device="cpu").manual_seed(case.input_seed + 100)
@@ -134,6 +179,10 @@ def main(argv=None):
         g = golden_sampler(case)
         torch.save(g, GOLDEN / f"sampler_{case.name}.pt")
         print(f"sampler_{case.name}.pt rms={g['x_final'].pow(2).mean().sqrt():.4f} idx={g['timestep_indices']}")
+    if not only or "vae" in only:
+        g = golden_vae_decode()
+        torch.save(g, GOLDEN / "vae_decode_small.pt")
+        print(f"vae_decode_small.pt {tuple(g['image'].shape)} rms={g['image'].pow(2).mean().sqrt():.4f}")
     # 25-step (the YAML's count, with use_last_frame share-noise init = BASELINE config 4) and 50-step (BASELINE
     # config 2) reference loops on the GPU-runnable head_dim-64 model, with the per-step trajectory
     for steps, ulf in ((25, True), (50, False)):

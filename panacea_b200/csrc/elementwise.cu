@@ -245,6 +245,54 @@ __global__ void scale_dup_kernel(const float* __restrict__ x, float* __restrict_
   }
 }
 
+// ---------------------------------------------------------------- row softmax, fp32 scores -> bf16 probabilities
+// The single-head, C-wide attention of the VAE mid block (reference model.py:374-414: SDPA over all h*w tokens with
+// head_dim = C = 512) is run as GEMMs (S = q k^T, O = P v) around this kernel: out[r, :] = softmax(scale * in[r, :]).
+// One CTA per row; the row's exponentials are kept in shared memory between the sum and the normalised store.
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int N,
+                                                           long long ld_in, long long ld_out, float scale_log2) {
+  extern __shared__ float sm_row[];
+  __shared__ float red[8];
+  const float* src = in + (long long)blockIdx.x * ld_in;
+  __nv_bfloat16* dst = out + (long long)blockIdx.x * ld_out;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float m = -INFINITY;
+  for (int i = threadIdx.x * 4; i < N; i += 1024) {
+    const float4 v = *reinterpret_cast<const float4*>(src + i);
+    *reinterpret_cast<float4*>(sm_row + i) = v;
+    m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+  __syncthreads();
+  const float nm = -m * scale_log2;
+  float s = 0.f;
+  for (int i = threadIdx.x * 4; i < N; i += 1024) {
+    float4 v = *reinterpret_cast<float4*>(sm_row + i);
+    v.x = exp2f(fmaf(v.x, scale_log2, nm)); v.y = exp2f(fmaf(v.y, scale_log2, nm));
+    v.z = exp2f(fmaf(v.z, scale_log2, nm)); v.w = exp2f(fmaf(v.w, scale_log2, nm));
+    *reinterpret_cast<float4*>(sm_row + i) = v;
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  s = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) s += red[w];
+  const float inv = 1.f / s;
+  for (int i = threadIdx.x * 4; i < N; i += 1024) {
+    const float4 v = *reinterpret_cast<float4*>(sm_row + i);
+    *reinterpret_cast<uint2*>(dst + i) = make_uint2(pack_bf16x2(v.x * inv, v.y * inv), pack_bf16x2(v.z * inv, v.w * inv));
+  }
+}
+
 // ---------------------------------------------------------------- content fingerprint of a device buffer
 // Two order-independent 64-bit sums over the 32-bit words (plain sum, position-weighted sum). The conditioning cache of
 // the wrapper keys on CONTENT with it: tensor addresses are recycled by the allocator and the reference's guider
@@ -407,6 +455,21 @@ extern "C" int pn_fingerprint(const void* x, int64_t nbytes, uint64_t* out2, voi
   const size_t nwords = (size_t)nbytes / 4;
   fingerprint_kernel<<<grid_for(nwords), 256, 0, st>>>(reinterpret_cast<const uint32_t*>(x), nwords,
                                                       reinterpret_cast<unsigned long long*>(out2));
+  PN_CHECK_CUDA(cudaGetLastError());
+  return PN_OK;
+}
+
+extern "C" int pn_softmax_rows(const float* in, void* out_bf16, int64_t rows, int64_t N, int64_t ld_in, int64_t ld_out, float scale,
+                               void* stream_v) {
+  PN_REQUIRE(in && out_bf16 && rows > 0 && N > 0 && N % 4 == 0 && ld_in >= N && ld_out >= N && ld_in % 4 == 0 && ld_out % 4 == 0,
+             "pn_softmax_rows: bad arguments");
+  PN_REQUIRE(N * 4 <= 200 * 1024, "pn_softmax_rows: N=%lld exceeds the shared-memory row buffer", (long long)N);
+  PN_REQUIRE(rows < (1ll << 31), "pn_softmax_rows: too many rows");
+  const size_t smem = (size_t)N * sizeof(float);
+  const int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&softmax_rows_kernel), smem);
+  if (rc != PN_OK) return rc;
+  softmax_rows_kernel<<<(unsigned)rows, 256, smem, reinterpret_cast<cudaStream_t>(stream_v)>>>(
+      in, reinterpret_cast<__nv_bfloat16*>(out_bf16), (int)N, ld_in, ld_out, scale * 1.4426950408889634f);
   PN_CHECK_CUDA(cudaGetLastError());
   return PN_OK;
 }

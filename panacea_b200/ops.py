@@ -369,6 +369,15 @@ class NativeOps:
         self.launches += 1
         return x
 
+    def softmax_rows(self, s, scale):
+        """fp32 [rows, N] -> bf16 [rows, N] = softmax(scale * s) per row (VAE mid-block attention)."""
+        _req(s.is_cuda and s.dtype == F32 and s.dim() == 2 and s.is_contiguous() and s.shape[1] % 4 == 0, "softmax_rows: fp32 [rows, N]")
+        out = torch.empty(s.shape, device=s.device, dtype=BF16)
+        _lib.check(self.lib.pn_softmax_rows(_ptr(s), _ptr(out), s.shape[0], s.shape[1], s.stride(0), out.stride(0), float(scale),
+                                           _stream()), "pn_softmax_rows")
+        self.launches += 1
+        return out
+
     def fingerprint(self, x):
         """(sum, weighted sum) of the 32-bit words of a contiguous CUDA tensor, as Python ints (synchronises)."""
         _req(x.is_cuda and x.is_contiguous() and (x.numel() * x.element_size()) % 4 == 0, "fingerprint: contiguous CUDA tensor")

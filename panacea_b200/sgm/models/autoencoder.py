@@ -1,35 +1,91 @@
-"""First stage (VAE) stand-in behind the reference's interface (sgm/models/autoencoder.py:333-373,
-`AutoencoderKLInferenceWrapper.encode / decode`, `post_quant_conv`). The KL autoencoder is row N2 of SURVEY.md
-section 8f (out of the hot path; BASELINE.json configs[3] allows a random-init stub): this class keeps the tensor contract
-— images [n, 3, 8h, 8w] in [-1, 1]  <->  latents [n, 4, h, w] — with a random-init 8x8 patch projection, so the engine
-glue, the gather of decoded frames and the frame writers can run end to end. It is NOT a trained VAE."""
+"""First stage behind the reference's interface (sgm/models/autoencoder.py:333-373, `AutoencoderKLInferenceWrapper`).
+
+* `decode(z)` — the KL autoencoder's DECODER runs natively on the hot path's kernels
+  (`panacea_b200.vae.VAEDecoderEngine`); parameters live under the reference's state-dict names (`decoder.*`,
+  `post_quant_conv.*`), so an SD-2.1 VAE checkpoint loads unchanged (`load_state_dict(strict=False)`).
+* `encode(x)` — the ENCODER is used once per sample on the image-condition frame; it is not built here. It is a
+  deterministic random-init 8x8 patch projection with the right tensor contract (BASELINE.json configs[3]: "random-init
+  VAE/CLIP stubs"), NOT a trained encoder; `encoder.*` / `quant_conv.*` checkpoint keys are ignored."""
 from __future__ import annotations
+
+import math
 
 import torch
 import torch.nn as nn
+
+from ...vae import VAEDecoderEngine, decoder_param_spec
 
 
 class AutoencoderKLInferenceWrapper(nn.Module):
     def __init__(self, embed_dim=4, ddconfig=None, lossconfig=None, monitor=None, seed: int = 1234, **kwargs):
         super().__init__()
-        dd = ddconfig or {}
-        self.in_channels = dd.get("in_channels", 3)
-        self.z_channels = dd.get("z_channels", embed_dim)
-        self.factor = 2 ** (len(dd.get("ch_mult", [1, 2, 4, 4])) - 1)           # 8x spatial compression
+        dd = dict(ddconfig or {})
+        dd.setdefault("ch", 128); dd.setdefault("ch_mult", [1, 2, 4, 4]); dd.setdefault("num_res_blocks", 2)
+        dd.setdefault("z_channels", embed_dim); dd.setdefault("out_ch", 3); dd.setdefault("in_channels", 3)
+        self.ddconfig, self.embed_dim = dd, embed_dim
+        self.factor = 2 ** (len(dd["ch_mult"]) - 1)
         g = torch.Generator().manual_seed(seed)
-        f, ci, cz = self.factor, self.in_channels, self.z_channels
-        self.quant_conv = nn.Conv2d(ci, cz, f, stride=f)                         # patch projection (mean of the posterior)
-        self.post_quant_conv = nn.Conv2d(cz, cz, 1)
-        self.decoder = nn.ConvTranspose2d(cz, ci, f, stride=f)
+        self._spec = decoder_param_spec(dd, embed_dim)
+        self._attr = {k: "p__" + k.replace(".", "__") for k in self._spec}
+        for k, shape in self._spec.items():
+            p = torch.empty(shape)
+            if k.endswith(".bias"):
+                p.zero_()
+            elif len(shape) == 1:
+                p.fill_(1.0)
+            else:
+                p.copy_(torch.randn(shape, generator=g) * (1.0 / math.sqrt(math.prod(shape[1:]))))
+            self.register_parameter(self._attr[k], nn.Parameter(p, requires_grad=False))
+        # encoder stand-in (see the module docstring)
+        f, ci, cz = self.factor, dd["in_channels"], dd["z_channels"]
+        self.stub_encoder = nn.Conv2d(ci, cz, f, stride=f)
         with torch.no_grad():
-            for p in self.parameters():
+            for p in self.stub_encoder.parameters():
                 p.copy_(torch.randn(p.shape, generator=g) * (1.0 / max(p[0].numel(), 1)) ** 0.5)
+        self._engine = None
+        self._version, self._packed = 0, -1
+
+    # --- reference key names
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        for k, a in self._attr.items():
+            p = getattr(self, a)
+            destination[prefix + k] = p if keep_vars else p.detach()
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        for k, a in self._attr.items():
+            if prefix + k in state_dict:
+                with torch.no_grad():
+                    getattr(self, a).copy_(state_dict[prefix + k])
+            else:
+                missing_keys.append(prefix + k)
+        self._version += 1
+
+    def _apply(self, fn, recurse=True):
+        r = super()._apply(fn, recurse)
+        self._version += 1
+        return r
+
+    @property
+    def post_quant_conv(self):                  # the reference reads `.post_quant_conv.weight.dtype` (diffusion.py:140)
+        return type("PQ", (), {"weight": getattr(self, self._attr["post_quant_conv.weight"])})()
+
+    def decoder_parameters(self) -> dict:
+        return {k: getattr(self, a) for k, a in self._attr.items()}
 
     @torch.no_grad()
     def encode(self, x):
-        """autoencoder.py:333-350 returns a posterior sample; the stub returns its mean (deterministic)."""
-        return self.quant_conv(x.float())
+        """Stand-in for autoencoder.py:366-368 (posterior sample of the KL encoder): deterministic patch projection."""
+        return self.stub_encoder(x.float())
 
     @torch.no_grad()
     def decode(self, z):
-        return torch.tanh(self.decoder(self.post_quant_conv(z.float())))
+        """autoencoder.py:362-365 on the sm_100a kernels (no CPU path)."""
+        if not z.is_cuda:
+            raise RuntimeError("panacea_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+        if self._engine is None:
+            from ...ops import NativeOps
+            self._engine = VAEDecoderEngine(self.ddconfig, NativeOps(), self.embed_dim)
+        if self._packed != self._version:
+            self._engine.pack(self.decoder_parameters())
+            self._packed = self._version
+        return self._engine.decode(z)

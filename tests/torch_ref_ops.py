@@ -153,6 +153,9 @@ class TorchRefOps:
     def cast_operand(self, x):
         return x
 
+    def softmax_rows(self, s, scale):
+        return torch.softmax(s.float() * scale, dim=-1)
+
     def nchw_to_nhwc(self, x, out=None, ch_off=0):
         y = x.permute(0, 2, 3, 1)
         if out is None:
