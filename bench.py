@@ -207,6 +207,18 @@ def synth_inputs_host(seed):
     return {"hint": pin(hint), "concat": pin(concat), "c_txt": pin(c_txt), "uc_txt": pin(uc_txt), "noise": pin(noise)}
 
 
+def load_traffic():
+    """DRAM bytes per launch of the dominant kernel family from the committed ncu pass (tools/ncu_traffic.py)."""
+    cands = sorted((ROOT / "profiles").glob("r*_gemm_traffic.json"))
+    if not cands:
+        return None, None
+    try:
+        d = json.loads(cands[-1].read_text())
+        return d["dram_bytes_per_launch"], f"profiles/{cands[-1].name}: ncu dram__bytes_read.sum + dram__bytes_write.sum over the {d['launches']} gemm_tc launches of one eps-evaluation / launches"
+    except (OSError, ValueError, KeyError):
+        return None, None
+
+
 def profile_dominant_kernel(pipe, x_in, t_dev, cc):
     """One eager eps-eval with CUDA-event timing around every launch of the dominant kernel (the tcgen05 GEMM /
     implicit-conv kernel): achieved TFLOP/s = sum of algorithmic FLOPs / sum of launch durations."""
@@ -221,7 +233,13 @@ def profile_dominant_kernel(pipe, x_in, t_dev, cc):
         out = orig(a, w, **kw)
         e.record()
         rows = a.numel() // a.shape[-1]
-        recs.append((2.0 * rows * w.shape[0] * w.shape[1], s, e))
+        n_out = w.shape[0] // 2 if kw.get("geglu") else w.shape[0]
+        osz = 2 if kw.get("out_dtype", torch.float32) == torch.bfloat16 else 4
+        abytes = 2.0 * rows * a.shape[-1] + 2.0 * w.numel() + osz * rows * n_out        # A + W + out (algorithmic, once each)
+        for r in (kw.get("residual"), kw.get("residual2")):
+            if r is not None:
+                abytes += r.element_size() * rows * n_out
+        recs.append((2.0 * rows * w.shape[0] * w.shape[1], s, e, abytes))
         return out
 
     eng.eps(x_in, cc["concat"].float().contiguous(), t_dev)      # untimed eager pass (module load, allocator warm-up)
@@ -234,7 +252,7 @@ def profile_dominant_kernel(pipe, x_in, t_dev, cc):
         ops.gemm = orig
     flops = sum(r[0] for r in recs)
     secs = sum(r[1].elapsed_time(r[2]) for r in recs) * 1e-3
-    return flops, secs, len(recs)
+    return flops, secs, len(recs), sum(r[3] for r in recs)
 
 
 def run_ours(args) -> None:
@@ -345,7 +363,7 @@ def run_ours(args) -> None:
         log(f"gathered {len(gathered)} latent tensors of shape {tuple(x.shape)} on rank 0")
 
     # ---- dominant-kernel roofline (eager, per-launch CUDA events), launch count of one graphed eps-eval
-    flops, secs, n_gemm = profile_dominant_kernel(pipe, x_in, t_all[0], cc2)
+    flops, secs, n_gemm, algo_bytes = profile_dominant_kernel(pipe, x_in, t_all[0], cc2)
     l0 = ops.launches
     pipe.model.engine().eps(x_in, cc2["concat"].float().contiguous(), t_all[0])
     torch.cuda.synchronize()
@@ -367,6 +385,7 @@ def run_ours(args) -> None:
             pass
         peak = peaks.get("bf16_tflops_sustained", 1400.0)
         achieved = flops / secs / 1e12
+        traffic, traffic_src = load_traffic()
         value = world * K / (ms * 1e-3)
         line = {
             "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": max(Wm, 3),
@@ -380,7 +399,10 @@ def run_ours(args) -> None:
             "algorithmic_tflop_per_step": ALGO_TFLOP_PER_STEP,
             "achieved_tflops_whole_step": ALGO_TFLOP_PER_STEP * (K / (ms * 1e-3)),
             "roofline": {"bound": "tensor", "kernel": "pn::gemm_tc_kernel (tcgen05 GEMM / implicit conv, all launches of one eps-eval)",
-                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                         "traffic_unit": "bytes per launch (DRAM read + write)", "traffic_source": traffic_src,
+                         "algorithmic_bytes_per_launch": algo_bytes / max(n_gemm, 1),
+                         "algorithmic_flops_per_launch": flops / max(n_gemm, 1),
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1400",
                          "launches": n_gemm, "share_of_step": secs / (ms * 1e-3 / K),
                          "how": "sum of 2*M*N*K over the launches / sum of per-launch CUDA-event durations, eager pass after the timed region"},
