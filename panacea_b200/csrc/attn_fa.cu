@@ -1,4 +1,5 @@
-// tcgen05 flash attention for the decomposed-4D attention of Panacea (head_dim 64, bf16 operands, fp32 softmax).
+// tcgen05 flash attention for the decomposed-4D attention of Panacea (head_dim 64 — the reference config — or 80,
+// BASELINE.json configs[4]; bf16 operands, fp32 softmax).
 //
 // One kernel serves the three tensor-core attention variants; they differ only in which K/V tiles a query tile
 // visits, and every tile is a TMA box of ONE rank-5 tensor map over the token buffer [F, H, V, w, C]
@@ -27,17 +28,29 @@
 
 namespace pn {
 
-constexpr int FA_D = 64;
-constexpr int FA_STAGES = 4;
 constexpr int FA_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..5 softmax of tile A, 6..9 of tile B
-constexpr int FA_TILE_BYTES = 128 * 128;          // 128 rows x 64 bf16
-constexpr int FA_SMEM_Q = 0;                                        // [2 buffers][2 tiles]
-constexpr int FA_SMEM_K = 4 * FA_TILE_BYTES;
-constexpr int FA_SMEM_V = FA_SMEM_K + FA_STAGES * FA_TILE_BYTES;
-constexpr int FA_SMEM_BAR = FA_SMEM_V + FA_STAGES * FA_TILE_BYTES;
-constexpr int FA_SMEM_TOTAL = FA_SMEM_BAR + 512 + 1024;
-// tensor memory columns: S_A S_B (fp32, 128 each) | P_A P_B (bf16 pairs, 64 each) | O_A O_B (fp32, 64 each)
-constexpr uint32_t FA_TM_S = 0, FA_TM_P = 256, FA_TM_O = 384;
+constexpr int FA_TILE_BYTES = 128 * 128;          // 128 rows x 64 bf16 (128 B rows, 128B swizzle)
+constexpr int FA_XTILE_BYTES = 128 * 32;          // head_dim 80: the channels 64..79 of 128 rows (32 B rows, 32B swizzle)
+// Shared / tensor memory layout per head_dim. head_dim 80 is handled as a 64-channel part plus a 16-channel part (a
+// TMA box with a 128 B swizzle cannot be wider than 64 bf16): every Q/K/V tile has a second, 32 B-row tile; S gets a
+// fifth K = 16 MMA step on the 16-channel tiles and O = P V a second MMA of N = 16 per key step into O columns 64..79.
+template <int D>
+struct FaL {
+  static constexpr int STAGES = D == 64 ? 4 : 3;                     // K/V ring (227 KB of shared memory)
+  static constexpr int XB = D == 64 ? 0 : FA_XTILE_BYTES;
+  static constexpr int Q = 0;                                        // [2 buffers][2 tiles]
+  static constexpr int K = 4 * FA_TILE_BYTES;
+  static constexpr int V = K + STAGES * FA_TILE_BYTES;
+  static constexpr int QX = V + STAGES * FA_TILE_BYTES;
+  static constexpr int KX = QX + 4 * XB;
+  static constexpr int VX = KX + STAGES * XB;
+  static constexpr int BAR = VX + STAGES * XB;
+  static constexpr int TOTAL = BAR + 512 + 1024;
+  // tensor memory columns. d = 64: S_A S_B (fp32, 128 each) | P_A P_B (bf16 pairs, 64 each) | O_A O_B (fp32, 64 each);
+  // d = 80 (key blocks of <= 112 keys): S 2 x 112 | P 2 x 56 | O 2 x 80 = 496 columns.
+  static constexpr uint32_t S_STRIDE = D == 64 ? 128 : 112, P_BASE = D == 64 ? 256 : 224, P_STRIDE = D == 64 ? 64 : 56;
+  static constexpr uint32_t O_BASE = D == 64 ? 384 : 336, O_STRIDE = D;
+};
 // PN_ATTN_DEBUG timing experiments exist only in diagnostics builds (-DPN_GEMM_ROLE_TIMERS, see build.py)
 #ifdef PN_GEMM_ROLE_TIMERS
 constexpr bool kFaExperiments = true;
@@ -50,6 +63,7 @@ struct FaParams {
   CUtensorMap mapQ;
   CUtensorMap mapK;
   CUtensorMap mapV;
+  CUtensorMap mapQx, mapKx, mapVx;   // head_dim 80: 16-channel boxes (32B swizzle) of the same tensors
   int heads;
   int F, H, V, W;              // query token grid
   int qw, qh, tiles_x, tiles_y;
@@ -91,11 +105,14 @@ __device__ __forceinline__ FaItem fa_decode(const FaParams& p, int item) {
 // NCH: number of 16-column chunks of a key block (kv_n / 16) fixed at compile time for the shapes of the network
 // (7 = 112 keys per block at 32x56 views, 8 = 128 keys at 32x64 views, 5 = the 77 text keys, 2 = the 4x7 middle block);
 // 0 = read it from the parameters (any other shape).
-template <bool MASK, int NCH>
+template <bool MASK, int NCH, int D>
 __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_constant__ FaParams p) {
+  using L = FaL<D>;
+  constexpr int FA_STAGES = L::STAGES;
+  constexpr int FA_D = D;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_align1024(smem_raw);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FA_SMEM_BAR);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR);
   uint64_t* q_full = bars;                     // [2]
   uint64_t* q_empty = bars + 2;                // [2]
   uint64_t* k_full = bars + 4;                 // [FA_STAGES]
@@ -114,13 +131,14 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
   // zero Q/K/V staging once: rows a TMA box does not cover (kv_rows..kv_n) must read as 0, never as stale NaNs
   {
     uint4* z = reinterpret_cast<uint4*>(smem);
-    for (int i = threadIdx.x; i < FA_SMEM_BAR / 16; i += FA_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < L::BAR / 16; i += FA_THREADS) z[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.mapQ);
     tma_prefetch_desc(&p.mapK);
     tma_prefetch_desc(&p.mapV);
+    if (D == 80) { tma_prefetch_desc(&p.mapQx); tma_prefetch_desc(&p.mapKx); tma_prefetch_desc(&p.mapVx); }
     for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
     for (int i = 0; i < FA_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); mbar_init(&kv_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
@@ -136,12 +154,13 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_prologue_done();
 
   if (warp == 0) {
     // ===================== TMA producer (warp-wide loop, TMA issue under elect.sync) =====================
     {
-      const uint32_t q_bytes = (uint32_t)(p.qw * p.qh) * 128u;
-      const uint32_t kv_bytes = (uint32_t)p.kv_rows * 128u;
+      const uint32_t q_bytes = (uint32_t)(p.qw * p.qh) * (D == 80 ? 160u : 128u);
+      const uint32_t kv_bytes = (uint32_t)p.kv_rows * (D == 80 ? 160u : 128u);
       int g = 0, it = 0;
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
         const FaItem t = fa_decode(p, item);
@@ -151,8 +170,11 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
           mbar_arrive_expect_tx(&q_full[qb], t.has_b ? 2 * q_bytes : q_bytes);
           for (int sl = 0; sl < (t.has_b ? 2 : 1); ++sl) {
             const int ti = t.t0 + sl;
-            tma_load_5d(smem + FA_SMEM_Q + (qb * 2 + sl) * FA_TILE_BYTES, &p.mapQ, &q_full[qb], t.head * FA_D,
+            tma_load_5d(smem + L::Q + (qb * 2 + sl) * FA_TILE_BYTES, &p.mapQ, &q_full[qb], t.head * FA_D,
                         (ti % p.tiles_x) * p.qw, t.view, (ti / p.tiles_x) * p.qh, t.frame);
+            if (D == 80)
+              tma_load_5d(smem + L::QX + (qb * 2 + sl) * FA_XTILE_BYTES, &p.mapQx, &q_full[qb], t.head * FA_D + 64,
+                          (ti % p.tiles_x) * p.qw, t.view, (ti / p.tiles_x) * p.qh, t.frame);
           }
         }
         const int kv_frame = t.frame / p.kv_frame_div;
@@ -163,9 +185,11 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
           mbar_wait(&kv_empty[st], (uint32_t)(((g / FA_STAGES) & 1) ^ 1));
           if (elect_one()) {
             mbar_arrive_expect_tx(&k_full[st], kv_bytes);
-            tma_load_5d(smem + FA_SMEM_K + st * FA_TILE_BYTES, &p.mapK, &k_full[st], t.head * FA_D, 0, kvv, yb * p.kh, kv_frame);
+            tma_load_5d(smem + L::K + st * FA_TILE_BYTES, &p.mapK, &k_full[st], t.head * FA_D, 0, kvv, yb * p.kh, kv_frame);
+            if (D == 80) tma_load_5d(smem + L::KX + st * FA_XTILE_BYTES, &p.mapKx, &k_full[st], t.head * FA_D + 64, 0, kvv, yb * p.kh, kv_frame);
             mbar_arrive_expect_tx(&v_full[st], kv_bytes);
-            tma_load_5d(smem + FA_SMEM_V + st * FA_TILE_BYTES, &p.mapV, &v_full[st], t.head * FA_D, 0, kvv, yb * p.kh, kv_frame);
+            tma_load_5d(smem + L::V + st * FA_TILE_BYTES, &p.mapV, &v_full[st], t.head * FA_D, 0, kvv, yb * p.kh, kv_frame);
+            if (D == 80) tma_load_5d(smem + L::VX + st * FA_XTILE_BYTES, &p.mapVx, &v_full[st], t.head * FA_D + 64, 0, kvv, yb * p.kh, kv_frame);
           }
           if (++yb == p.kv_yblocks) { yb = 0; ++vi; }
         }
@@ -175,12 +199,18 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
     // ===================== UMMA issuer (warp-wide loop; MMAs and commits under elect.sync, descriptors = base + k) ====
     {
       const uint32_t idesc_s = umma_idesc_bf16(128, p.kv_n, 0, 0);      // S = Q K^T : both K-major
-      const uint32_t idesc_pv = umma_idesc_bf16(128, FA_D, 0, 1);       // PV: A = P (tensor memory), B = V MN-major
+      const uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);         // PV: A = P (tensor memory), B = V MN-major
+      const uint32_t idesc_pvx = umma_idesc_bf16(128, 16, 0, 1);        // head_dim 80: channels 64..79
       const int ksteps_pv = NCH > 0 ? NCH : p.kv_n / 16;
-      const uint64_t dQ0 = umma_smem_desc(smem_u32(smem + FA_SMEM_Q), 16, 1024);
-      const uint64_t dK0 = umma_smem_desc(smem_u32(smem + FA_SMEM_K), 16, 1024);
-      const uint64_t dV0 = umma_smem_desc(smem_u32(smem + FA_SMEM_V), 1024, 1024);
+      const uint64_t dQ0 = umma_smem_desc(smem_u32(smem + L::Q), 16, 1024);
+      const uint64_t dK0 = umma_smem_desc(smem_u32(smem + L::K), 16, 1024);
+      const uint64_t dV0 = umma_smem_desc(smem_u32(smem + L::V), 1024, 1024);
+      // 16-channel tiles: 32 B rows, 32B swizzle, 8-row groups 256 B apart (K-major for Q/K, MN-major for V)
+      const uint64_t dQx0 = umma_smem_desc_sw32(smem_u32(smem + L::QX), 16, 256);
+      const uint64_t dKx0 = umma_smem_desc_sw32(smem_u32(smem + L::KX), 16, 256);
+      const uint64_t dVx0 = umma_smem_desc_sw32(smem_u32(smem + L::VX), 256, 256);
       constexpr uint64_t TILE_STEP = FA_TILE_BYTES >> 4;                // start-address field is in 16-byte units
+      constexpr uint64_t XTILE_STEP = FA_XTILE_BYTES >> 4;
       uint32_t n_s[2] = {0, 0}, n_pv[2] = {0, 0};                       // blocks issued per tile slot
       bool pend = false, pend_b = false;
       int pend_g = 0, pend_j = 0;
@@ -195,10 +225,15 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
             mbar_wait(&p_full[sl], n_pv[sl] & 1);
             tc_fence_after();
             if (elect_one()) {
-              const uint32_t tO = tmem_base + FA_TM_O + sl * 64, tP = tmem_base + FA_TM_P + sl * 64;
+              const uint32_t tO = tmem_base + L::O_BASE + sl * L::O_STRIDE, tP = tmem_base + L::P_BASE + sl * L::P_STRIDE;
+              const uint64_t dVx = dVx0 + XTILE_STEP * st;
 #pragma unroll
-              for (int k = 0; k < 8; ++k)   // 16 keys per step: 8 packed columns of P, 16 rows (128 B each) of V
-                if (k < ksteps_pv && dbgmode != 2) umma_f16_ts(tO, tP + 8 * k, dV + 128 * k, idesc_pv, (pend_j > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < 8; ++k) {  // 16 keys per step: 8 packed columns of P, 16 rows (128 B each) of V
+                if (k < ksteps_pv && dbgmode != 2) {
+                  umma_f16_ts(tO, tP + 8 * k, dV + 128 * k, idesc_pv, (pend_j > 0 || k > 0) ? 1u : 0u);
+                  if (D == 80) umma_f16_ts(tO + 64, tP + 8 * k, dVx + 32 * k, idesc_pvx, (pend_j > 0 || k > 0) ? 1u : 0u);
+                }
+              }
               umma_commit(&pv_done[sl]);
               if (sl == 1 || !pend_b) umma_commit(&kv_empty[st]);
             }
@@ -224,8 +259,10 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
                 const uint64_t dQ = dQ0 + TILE_STEP * (qb * 2 + sl);
                 if (dbgmode != 2) {
 #pragma unroll
-                  for (int k = 0; k < FA_D / 16; ++k)
-                    umma_f16_ss(tmem_base + FA_TM_S + sl * 128, dQ + 2 * k, dK + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+                  for (int k = 0; k < 4; ++k)
+                    umma_f16_ss(tmem_base + sl * L::S_STRIDE, dQ + 2 * k, dK + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+                  if (D == 80)
+                    umma_f16_ss(tmem_base + sl * L::S_STRIDE, dQx0 + XTILE_STEP * (qb * 2 + sl), dKx0 + XTILE_STEP * st, idesc_s, 1u);
                 }
                 umma_commit(&s_full[sl]);
                 // every S MMA reading this Q pair has retired
@@ -246,9 +283,9 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
     const int lane_grp = warp & 3;                                  // TMEM lane quarter this warp may access
     const int row = lane_grp * 32 + lane;
     const uint32_t lane_addr = uint32_t(lane_grp * 32) << 16;
-    const uint32_t tS = tmem_base + lane_addr + FA_TM_S + sl * 128;
-    const uint32_t tP = tmem_base + lane_addr + FA_TM_P + sl * 64;
-    const uint32_t tO = tmem_base + lane_addr + FA_TM_O + sl * 64;
+    const uint32_t tS = tmem_base + lane_addr + sl * L::S_STRIDE;
+    const uint32_t tP = tmem_base + lane_addr + L::P_BASE + sl * L::P_STRIDE;
+    const uint32_t tO = tmem_base + lane_addr + L::O_BASE + sl * L::O_STRIDE;
     const int nchunk = NCH > 0 ? NCH : p.kv_n / 16;
     const float c = p.scale_log2;
     const f32x2 c2 = f2_splat(c);
@@ -270,6 +307,21 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             *reinterpret_cast<uint4*>(dst + hh * 32 + i * 8) = make_uint4(
+                pack_bf16x2(__uint_as_float(o[i * 8 + 0]) * inv, __uint_as_float(o[i * 8 + 1]) * inv),
+                pack_bf16x2(__uint_as_float(o[i * 8 + 2]) * inv, __uint_as_float(o[i * 8 + 3]) * inv),
+                pack_bf16x2(__uint_as_float(o[i * 8 + 4]) * inv, __uint_as_float(o[i * 8 + 5]) * inv),
+                pack_bf16x2(__uint_as_float(o[i * 8 + 6]) * inv, __uint_as_float(o[i * 8 + 7]) * inv));
+          }
+        }
+      }
+      if (D == 80) {                  // channels 64..79
+        uint32_t o[16];
+        tmem_ld_32x16(tO + 64, o);
+        tmem_ld_wait();
+        if (ok) {
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            *reinterpret_cast<uint4*>(dst + 64 + i * 8) = make_uint4(
                 pack_bf16x2(__uint_as_float(o[i * 8 + 0]) * inv, __uint_as_float(o[i * 8 + 1]) * inv),
                 pack_bf16x2(__uint_as_float(o[i * 8 + 2]) * inv, __uint_as_float(o[i * 8 + 3]) * inv),
                 pack_bf16x2(__uint_as_float(o[i * 8 + 4]) * inv, __uint_as_float(o[i * 8 + 5]) * inv),
@@ -376,6 +428,14 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
             for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
             tmem_st_32x32(tO + hh * 32, o);
           }
+          if (D == 80) {
+            uint32_t o[16];
+            tmem_ld_32x16(tO + 64, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x16(tO + 64, o);
+          }
         }
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) {
@@ -413,8 +473,10 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
 
 typedef void (*FaKernel)(const FaParams);
 static FaKernel fa_kernels[10] = {
-    attn_fa_kernel<false, 0>, attn_fa_kernel<false, 2>, attn_fa_kernel<false, 5>, attn_fa_kernel<false, 7>, attn_fa_kernel<false, 8>,
-    attn_fa_kernel<true, 0>,  attn_fa_kernel<true, 2>,  attn_fa_kernel<true, 5>,  attn_fa_kernel<true, 7>,  attn_fa_kernel<true, 8>};
+    attn_fa_kernel<false, 0, 64>, attn_fa_kernel<false, 2, 64>, attn_fa_kernel<false, 5, 64>, attn_fa_kernel<false, 7, 64>, attn_fa_kernel<false, 8, 64>,
+    attn_fa_kernel<true, 0, 64>,  attn_fa_kernel<true, 2, 64>,  attn_fa_kernel<true, 5, 64>,  attn_fa_kernel<true, 7, 64>,  attn_fa_kernel<true, 8, 64>};
+// head_dim 80 (BASELINE.json configs[4] sweep): the 112-key block of 32x56 views, and the generic chunk count
+static FaKernel fa_kernels80[3] = {attn_fa_kernel<false, 7, 80>, attn_fa_kernel<false, 0, 80>, attn_fa_kernel<true, 0, 80>};
 
 }  // namespace pn
 
@@ -423,7 +485,9 @@ using namespace pn;
 extern "C" int pn_attention(const pn_attn_args* a, void* stream_v) {
   if (a == nullptr) return fail(PN_ERR_INVALID, "pn_attention: null args");
   PN_REQUIRE(a->q && a->k && a->v && a->out, "pn_attention: null tensor pointer");
-  PN_REQUIRE(a->head_dim == FA_D, "pn_attention: head_dim %d unsupported (64 only)", a->head_dim);
+  PN_REQUIRE(a->head_dim == 64 || a->head_dim == 80, "pn_attention: head_dim %d unsupported (64 or 80)", a->head_dim);
+  const int FA_D = a->head_dim;
+  const int max_keys = FA_D == 80 ? 112 : 128;      // head_dim 80: S 2 x 112 + P 2 x 56 + O 2 x 80 tensor-memory columns
   PN_REQUIRE(a->heads > 0 && a->F > 0 && a->H > 0 && a->V > 0 && a->V <= 8 && a->W > 0, "pn_attention: bad query geometry");
   PN_REQUIRE(a->Hk > 0 && a->Vk > 0 && a->Vk <= 8 && a->Wk > 0 && a->kv_frame_div > 0, "pn_attention: bad key geometry");
   PN_REQUIRE(a->q_ld % 8 == 0 && a->kv_ld % 8 == 0 && a->out_ld % 8 == 0, "pn_attention: token strides must be multiples of 8");
@@ -444,7 +508,8 @@ extern "C" int pn_attention(const pn_attn_args* a, void* stream_v) {
   // key block: full key-view width (must fit one block row-wise), rows = largest divisor of Hk with <= 128 keys
   PN_REQUIRE(a->Wk <= 128, "pn_attention: key view width %lld > 128 unsupported", (long long)a->Wk);
   p.kw = (int)a->Wk;
-  int kh = 128 / p.kw;
+  PN_REQUIRE(p.kw <= max_keys, "pn_attention: key view width %lld > %d unsupported at head_dim %d", (long long)a->Wk, max_keys, FA_D);
+  int kh = max_keys / p.kw;
   if (kh > a->Hk) kh = (int)a->Hk;
   while (kh > 1 && (a->Hk % kh) != 0) --kh;
   p.kh = kh;
@@ -478,6 +543,11 @@ extern "C" int pn_attention(const pn_attn_args* a, void* stream_v) {
     const uint32_t box[5] = {64u, (uint32_t)p.qw, 1u, (uint32_t)p.qh, 1u};
     int rc = cached_tmap_bf16(&p.mapQ, a->q, 5, dims, str, box, 128);
     if (rc != PN_OK) return rc;
+    if (FA_D == 80) {
+      const uint32_t boxx[5] = {16u, (uint32_t)p.qw, 1u, (uint32_t)p.qh, 1u};
+      rc = cached_tmap_bf16(&p.mapQx, a->q, 5, dims, str, boxx, 32);
+      if (rc != PN_OK) return rc;
+    }
   }
   {
     const uint64_t Fk = (uint64_t)((a->F + a->kv_frame_div - 1) / a->kv_frame_div);
@@ -489,6 +559,13 @@ extern "C" int pn_attention(const pn_attn_args* a, void* stream_v) {
     if (rc != PN_OK) return rc;
     rc = cached_tmap_bf16(&p.mapV, a->v, 5, dims, str, box, 128);
     if (rc != PN_OK) return rc;
+    if (FA_D == 80) {
+      const uint32_t boxx[5] = {16u, (uint32_t)p.kw, 1u, (uint32_t)p.kh, 1u};
+      rc = cached_tmap_bf16(&p.mapKx, a->k, 5, dims, str, boxx, 32);
+      if (rc != PN_OK) return rc;
+      rc = cached_tmap_bf16(&p.mapVx, a->v, 5, dims, str, boxx, 32);
+      if (rc != PN_OK) return rc;
+    }
   }
   p.tiles_per_group = p.tiles_x * p.tiles_y;
   p.pairs = (p.tiles_per_group + 1) / 2;
@@ -498,12 +575,13 @@ extern "C" int pn_attention(const pn_attn_args* a, void* stream_v) {
   const int grid = items < sm_count() ? (int)items : sm_count();
   const int nch = p.kv_n / 16;
   const int slot = nch == 8 ? 4 : nch == 7 ? 3 : nch == 5 ? 2 : nch == 2 ? 1 : 0;
-  const FaKernel kern = fa_kernels[(p.kv_rows < p.kv_n ? 5 : 0) + slot];
+  const bool masked = p.kv_rows < p.kv_n;
+  const FaKernel kern = FA_D == 80 ? fa_kernels80[masked ? 2 : (nch == 7 ? 0 : 1)] : fa_kernels[(masked ? 5 : 0) + slot];
+  const size_t smem_total = FA_D == 80 ? FaL<80>::TOTAL : FaL<64>::TOTAL;
   {
-    const int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), FA_SMEM_TOTAL);
+    const int rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem_total);
     if (rc != PN_OK) return rc;
   }
-  kern<<<grid, FA_THREADS, FA_SMEM_TOTAL, reinterpret_cast<cudaStream_t>(stream_v)>>>(p);
-  PN_CHECK_CUDA(cudaGetLastError());
+  PN_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(FA_THREADS), smem_total, reinterpret_cast<cudaStream_t>(stream_v), 1, p));
   return PN_OK;
 }

@@ -15,7 +15,8 @@ namespace pn {
 
 constexpr int TA_MAXT = 16;
 constexpr int TA_WARPS = 4;
-constexpr int TA_PITCH = 72;  // 144 B rows: 16-B aligned, 8 consecutive rows cover all 32 banks (conflict-free ldmatrix)
+// row pitch D + 8 elements (144 B for head_dim 64, 176 B for 80): 16-B aligned, 8 consecutive rows start in 8 different
+// 4-bank groups (conflict-free ldmatrix)
 
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* p) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -34,11 +35,15 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4],
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
+template <int D>
 __global__ void __launch_bounds__(TA_WARPS * 32) attn_temporal_kernel(const __nv_bfloat16* __restrict__ q,
                                                                       const __nv_bfloat16* __restrict__ k,
                                                                       const __nv_bfloat16* __restrict__ v,
                                                                       __nv_bfloat16* __restrict__ out, int nb, int T, int P,
                                                                       int heads, long long ld, long long out_ld, float scale) {
+  pdl_prologue_done();
+  constexpr int TA_PITCH = D + 8;
+  constexpr int RCH = D / 8;            // 16-byte chunks per row
   __shared__ __align__(16) __nv_bfloat16 sq[TA_WARPS][TA_MAXT][TA_PITCH];   // Q rows, later the output rows
   __shared__ __align__(16) __nv_bfloat16 sk[TA_WARPS][TA_MAXT][TA_PITCH];
   __shared__ __align__(16) __nv_bfloat16 sv[TA_WARPS][TA_MAXT][TA_PITCH];
@@ -51,17 +56,17 @@ __global__ void __launch_bounds__(TA_WARPS * 32) attn_temporal_kernel(const __nv
   const int pix = (int)(bp % P);
   const int b = (int)(bp / P);
   // rows T..15 are MMA padding: they must be finite (0 * NaN would poison the valid rows of P V)
-  for (int i = lane; i < (TA_MAXT - T) * 8; i += 32) {
-    const int t = T + (i >> 3), ch = i & 7;
+  for (int i = lane; i < (TA_MAXT - T) * RCH; i += 32) {
+    const int t = T + i / RCH, ch = i % RCH;
     *reinterpret_cast<uint4*>(&sq[w][t][ch * 8]) = make_uint4(0, 0, 0, 0);
     *reinterpret_cast<uint4*>(&sk[w][t][ch * 8]) = make_uint4(0, 0, 0, 0);
     *reinterpret_cast<uint4*>(&sv[w][t][ch * 8]) = make_uint4(0, 0, 0, 0);
   }
-  // stage q,k,v rows: each row is 64 bf16 = 128 B = 8 x 16 B; lanes 0..7 -> row t, lanes 8..15 -> row t+1, ...
-  for (int i = lane; i < T * 8; i += 32) {
-    const int t = i >> 3, ch = i & 7;
+  // stage q,k,v rows: each row is D bf16 = RCH x 16 B; consecutive lanes take consecutive chunks
+  for (int i = lane; i < T * RCH; i += 32) {
+    const int t = i / RCH, ch = i % RCH;
     const long long tok = ((long long)(b * T + t) * P + pix);
-    const long long off = tok * ld + head * 64 + ch * 8;
+    const long long off = tok * ld + head * D + ch * 8;
     *reinterpret_cast<uint4*>(&sq[w][t][ch * 8]) = *reinterpret_cast<const uint4*>(q + off);
     *reinterpret_cast<uint4*>(&sk[w][t][ch * 8]) = *reinterpret_cast<const uint4*>(k + off);
     *reinterpret_cast<uint4*>(&sv[w][t][ch * 8]) = *reinterpret_cast<const uint4*>(v + off);
@@ -73,7 +78,7 @@ __global__ void __launch_bounds__(TA_WARPS * 32) attn_temporal_kernel(const __nv
   // ---- S = Q K^T (16 x 8*ntile), fp32
   float sacc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {
+  for (int kk = 0; kk < D / 16; ++kk) {
     uint32_t aq[4];
     ldmatrix_x4(aq, &sq[w][lane & 15][kk * 16 + (lane >> 4) * 8]);
 #pragma unroll
@@ -118,9 +123,9 @@ __global__ void __launch_bounds__(TA_WARPS * 32) attn_temporal_kernel(const __nv
   uint32_t ap[4] = {pack_bf16x2(sacc[0][0], sacc[0][1]), pack_bf16x2(sacc[0][2], sacc[0][3]),
                     pack_bf16x2(sacc[1][0], sacc[1][1]), pack_bf16x2(sacc[1][2], sacc[1][3])};
   __syncwarp();                                 // every lane has read its Q fragments: sq becomes the output staging
-  // ---- O = P V (16 x 64): 8 channel tiles of 8, V rows (keys) x channels read transposed
+  // ---- O = P V (16 x D): D/8 channel tiles of 8, V rows (keys) x channels read transposed
 #pragma unroll
-  for (int nd = 0; nd < 8; ++nd) {
+  for (int nd = 0; nd < D / 8; ++nd) {
     uint32_t bv[2];
     ldmatrix_x2_trans(bv, &sv[w][lane & 15][nd * 8]);
     float o[4] = {0.f, 0.f, 0.f, 0.f};
@@ -129,10 +134,10 @@ __global__ void __launch_bounds__(TA_WARPS * 32) attn_temporal_kernel(const __nv
     *reinterpret_cast<uint32_t*>(&sq[w][r0 + 8][nd * 8 + cq]) = pack_bf16x2(o[2] * inv1, o[3] * inv1);
   }
   __syncwarp();
-  for (int i = lane; i < T * 8; i += 32) {
-    const int t = i >> 3, ch = i & 7;
+  for (int i = lane; i < T * RCH; i += 32) {
+    const int t = i / RCH, ch = i % RCH;
     const long long tok = ((long long)(b * T + t) * P + pix);
-    *reinterpret_cast<uint4*>(out + tok * out_ld + head * 64 + ch * 8) = *reinterpret_cast<const uint4*>(&sq[w][t][ch * 8]);
+    *reinterpret_cast<uint4*>(out + tok * out_ld + head * D + ch * 8) = *reinterpret_cast<const uint4*>(&sq[w][t][ch * 8]);
   }
 }
 
@@ -144,17 +149,23 @@ extern "C" int pn_attention_temporal(const void* q, const void* k, const void* v
                                      int64_t pixels, int32_t heads, int32_t head_dim, int64_t ld, int64_t out_ld,
                                      float scale, void* stream_v) {
   PN_REQUIRE(q && k && v && out, "pn_attention_temporal: null pointer");
-  PN_REQUIRE(head_dim == 64, "pn_attention_temporal: head_dim %d unsupported (64 only)", head_dim);
+  PN_REQUIRE(head_dim == 64 || head_dim == 80, "pn_attention_temporal: head_dim %d unsupported (64 or 80)", head_dim);
   PN_REQUIRE(T >= 1 && T <= TA_MAXT, "pn_attention_temporal: T=%lld out of range 1..16", (long long)T);
   PN_REQUIRE(batch > 0 && pixels > 0 && heads > 0 && ld % 8 == 0 && out_ld % 2 == 0, "pn_attention_temporal: bad arguments");
   PN_REQUIRE(out_ld % 8 == 0, "pn_attention_temporal: out_ld must be a multiple of 8");
   const long long total = batch * pixels * heads;
   const long long blocks = (total + TA_WARPS - 1) / TA_WARPS;
   PN_REQUIRE(blocks < (1ll << 31), "pn_attention_temporal: grid too large");
-  attn_temporal_kernel<<<(unsigned)blocks, TA_WARPS * 32, 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
-      reinterpret_cast<const __nv_bfloat16*>(v), reinterpret_cast<__nv_bfloat16*>(out), (int)batch, (int)T, (int)pixels, heads,
-      ld, out_ld, scale);
+  if (head_dim == 64)
+    launch_kernel(attn_temporal_kernel<64>, dim3((unsigned)blocks), dim3(TA_WARPS * 32), 0, reinterpret_cast<cudaStream_t>(stream_v), 1,
+                  reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
+                  reinterpret_cast<const __nv_bfloat16*>(v), reinterpret_cast<__nv_bfloat16*>(out), (int)batch, (int)T, (int)pixels, heads,
+                  ld, out_ld, scale);
+  else
+    launch_kernel(attn_temporal_kernel<80>, dim3((unsigned)blocks), dim3(TA_WARPS * 32), 0, reinterpret_cast<cudaStream_t>(stream_v), 1,
+                  reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
+                  reinterpret_cast<const __nv_bfloat16*>(v), reinterpret_cast<__nv_bfloat16*>(out), (int)batch, (int)T, (int)pixels, heads,
+                  ld, out_ld, scale);
   PN_CHECK_CUDA(cudaGetLastError());
   return PN_OK;
 }

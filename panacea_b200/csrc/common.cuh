@@ -44,4 +44,35 @@ int sm_count();                                          // of the current devic
 // opt in to `bytes` of dynamic shared memory for `func` on the current device (once per device and size)
 int ensure_dyn_smem(const void* func, size_t bytes);
 
+// PN_PDL=1 enables programmatic dependent launch (off by default: measured no gain on the captured graph)
+bool pdl_enabled();
+
+// Launch with programmatic stream serialization (and optionally a thread-block cluster): the kernel must call
+// pdl_prologue_done() (ptx.cuh) before its first global-memory access.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[n].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  ++n;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = (unsigned)cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 }  // namespace pn

@@ -11,6 +11,7 @@ namespace pn {
 // ---------------------------------------------------------------- [F, A, B] -> out[f, b, off + a] (row stride ld)
 __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int A, int B, long long ld,
                                  int off) {
+  pdl_prologue_done();
   __shared__ float tile[32][33];
   const int f = blockIdx.z;
   const int b0 = blockIdx.x * 32, a0 = blockIdx.y * 32;
@@ -30,6 +31,7 @@ __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict
 // ---------------------------------------------------------------- nearest 2x upsample, fp32 -> GEMM operand
 template <int OP>
 __global__ void upsample2x_kernel(const float* __restrict__ x, void* __restrict__ y, int F, int H, int W, int C) {
+  pdl_prologue_done();
   const int c8n = C / 8;
   const size_t total = (size_t)F * (2 * H) * (2 * W) * c8n;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
@@ -50,6 +52,7 @@ __global__ void upsample2x_kernel(const float* __restrict__ x, void* __restrict_
 __global__ void concat_add_kernel(const float* __restrict__ h, const float* __restrict__ skip,
                                   const float* __restrict__ ctrl, float* __restrict__ out, long long rows, int C1,
                                   int C2) {
+  pdl_prologue_done();
   const int Ct = C1 + C2;
   const int c4n = Ct / 4;
   const size_t total = (size_t)rows * c4n;
@@ -71,6 +74,7 @@ __global__ void concat_add_kernel(const float* __restrict__ h, const float* __re
 }
 
 __global__ void add_inplace_kernel(float* __restrict__ x, const float* __restrict__ y, size_t n4) {
+  pdl_prologue_done();
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (size_t)gridDim.x * blockDim.x) {
     float4 a = reinterpret_cast<float4*>(x)[e];
     const float4 b = reinterpret_cast<const float4*>(y)[e];
@@ -82,6 +86,7 @@ __global__ void add_inplace_kernel(float* __restrict__ x, const float* __restric
 // fp32 [rows, C] -> GEMM operand [rows, C] (bf16) or [rows, 3C] (split3)
 template <int OP>
 __global__ void cast_operand_kernel(const float* __restrict__ x, void* __restrict__ y, size_t rows, int C) {
+  pdl_prologue_done();
   const int c4n = C / 4;
   const size_t n4 = rows * (size_t)c4n;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (size_t)gridDim.x * blockDim.x) {
@@ -96,6 +101,7 @@ __global__ void cast_operand_kernel(const float* __restrict__ x, void* __restric
 // gelu_erf(in[row, 32 b + 16 + i]) with the exact erf GELU of the reference (attention.py:97-99). Parity mode only.
 template <int OP>
 __global__ void geglu_operand_kernel(const float* __restrict__ in, void* __restrict__ y, size_t rows, int inner) {
+  pdl_prologue_done();
   const int c4n = inner / 4;
   const size_t n4 = rows * (size_t)c4n;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (size_t)gridDim.x * blockDim.x) {
@@ -118,6 +124,7 @@ __global__ void geglu_operand_kernel(const float* __restrict__ in, void* __restr
 // expression, so the arguments t * f_k are bit-identical to the reference's — t is up to 999, an ulp of f_k matters).
 __global__ void timestep_embedding_kernel(const long long* __restrict__ t, float* __restrict__ out, int n, int dim,
                                           const float* __restrict__ freqs) {
+  pdl_prologue_done();
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * half) return;
@@ -145,6 +152,7 @@ template <int MAXM, typename TW>
 __global__ void __launch_bounds__(128) linear_small_kernel(const float* __restrict__ x, const TW* __restrict__ W,
                                                            const float* __restrict__ bias, float* __restrict__ y, int M,
                                                            int N, int K, long long ldy, int silu_in, int silu_out) {
+  pdl_prologue_done();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int n0 = warp * 4;
@@ -192,6 +200,7 @@ __global__ void __launch_bounds__(128) linear_small_kernel(const float* __restri
 template <int OP>
 __global__ void im2col_s2_kernel(const float* __restrict__ x, void* __restrict__ out, int F, int H, int W, int C,
                                  int Ho, int Wo) {
+  pdl_prologue_done();
   const int c8n = C / 8;
   const size_t total = (size_t)F * Ho * Wo * 9 * c8n;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
@@ -221,6 +230,7 @@ __global__ void im2col_s2_kernel(const float* __restrict__ x, void* __restrict__
 __global__ void cfg_euler_kernel(float* __restrict__ x, const float* __restrict__ net2, float* __restrict__ x_in_next,
                                  size_t n, float sigma, float sigma_q, float sigma_next, float scale, float c_in_next,
                                  int net_is_denoised) {
+  pdl_prologue_done();
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
     const float xv = x[e];
     // denoiser.py:28 with EpsScaling: denoised = net * c_out + x * c_skip, c_out = -sigma_q, c_skip = 1
@@ -239,6 +249,7 @@ __global__ void cfg_euler_kernel(float* __restrict__ x, const float* __restrict_
 }
 
 __global__ void scale_dup_kernel(const float* __restrict__ x, float* __restrict__ out, size_t n, float s, int copies) {
+  pdl_prologue_done();
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
     const float v = x[e] * s;
     for (int c = 0; c < copies; ++c) out[(size_t)c * n + e] = v;
@@ -251,6 +262,7 @@ __global__ void scale_dup_kernel(const float* __restrict__ x, float* __restrict_
 // One CTA per row; the row's exponentials are kept in shared memory between the sum and the normalised store.
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int N,
                                                            long long ld_in, long long ld_out, float scale_log2) {
+  pdl_prologue_done();
   extern __shared__ float sm_row[];
   __shared__ float red[8];
   const float* src = in + (long long)blockIdx.x * ld_in;
@@ -298,6 +310,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
 // the wrapper keys on CONTENT with it: tensor addresses are recycled by the allocator and the reference's guider
 // rebuilds its torch.cat-ed dict every step, so neither identity nor address says whether the BEV hint / text changed.
 __global__ void fingerprint_kernel(const uint32_t* __restrict__ x, size_t nwords, unsigned long long* __restrict__ out2) {
+  pdl_prologue_done();
   unsigned long long s1 = 0ull, s2 = 0ull;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x) {
     const unsigned long long w = x[i];
@@ -332,7 +345,7 @@ extern "C" int pn_transpose_f32(const float* in, float* out, int64_t batch, int6
   PN_REQUIRE(in && out && batch > 0 && A > 0 && B > 0 && out_ld >= out_off + A, "pn_transpose_f32: bad arguments");
   PN_REQUIRE(batch <= 65535, "pn_transpose_f32: batch too large");
   dim3 grid((unsigned)((B + 31) / 32), (unsigned)((A + 31) / 32), (unsigned)batch);
-  transpose_kernel<<<grid, dim3(32, 8), 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(in, out, (int)A, (int)B, out_ld,
+  launch_kernel(transpose_kernel, dim3(grid), dim3(dim3(32, 8)), 0, reinterpret_cast<cudaStream_t>(stream_v), 1, in, out, (int)A, (int)B, out_ld,
                                                                                          (int)out_off);
   PN_CHECK_CUDA(cudaGetLastError());
   return PN_OK;
@@ -343,7 +356,7 @@ extern "C" int pn_upsample2x(const float* x, void* y, int64_t frames, int64_t H,
   PN_REQUIRE(x && y && frames > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "pn_upsample2x: bad arguments");
   PN_REQUIRE(operand_mode >= 0 && operand_mode <= 2, "pn_upsample2x: operand_mode %d", operand_mode);
   const size_t total = (size_t)frames * 4 * H * W * (C / 8);
-  PN_DISPATCH_OP(operand_mode, (upsample2x_kernel<OP><<<grid_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(
+  PN_DISPATCH_OP(operand_mode, (launch_kernel(upsample2x_kernel<OP>, dim3(grid_for(total)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream_v), 1, 
       x, y, (int)frames, (int)H, (int)W, (int)C)));
   PN_CHECK_CUDA(cudaGetLastError());
   return PN_OK;
@@ -353,7 +366,7 @@ extern "C" int pn_concat_add(const float* h, const float* skip, const float* ctr
                              int64_t C2, void* stream_v) {
   PN_REQUIRE(h && skip && out && rows > 0 && C1 % 4 == 0 && C2 % 4 == 0 && C1 > 0 && C2 > 0, "pn_concat_add: bad arguments");
   const size_t total = (size_t)rows * ((C1 + C2) / 4);
-  concat_add_kernel<<<grid_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(h, skip, ctrl, out, rows,
+  launch_kernel(concat_add_kernel, dim3(grid_for(total)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream_v), 1, h, skip, ctrl, out, rows,
                                                                                            (int)C1, (int)C2);
   PN_CHECK_CUDA(cudaGetLastError());
   return PN_OK;
@@ -361,7 +374,7 @@ extern "C" int pn_concat_add(const float* h, const float* skip, const float* ctr
 
 extern "C" int pn_add_inplace(float* x, const float* y, int64_t n, void* stream_v) {
   PN_REQUIRE(x && y && n > 0 && n % 4 == 0, "pn_add_inplace: bad arguments");
-  add_inplace_kernel<<<grid_for((size_t)n / 4), 256, 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(x, y, (size_t)n / 4);
+  launch_kernel(add_inplace_kernel, dim3(grid_for((size_t)n / 4)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream_v), 1, x, y, (size_t)n / 4);
   PN_CHECK_CUDA(cudaGetLastError());
   return PN_OK;
 }
@@ -370,7 +383,7 @@ extern "C" int pn_cast_operand(const float* x, void* y, int64_t rows, int64_t C,
   PN_REQUIRE(x && y && rows > 0 && C > 0 && C % 4 == 0, "pn_cast_operand: bad arguments");
   PN_REQUIRE(operand_mode == PN_OP_BF16 || operand_mode == PN_OP_SPLIT3, "pn_cast_operand: operand_mode %d", operand_mode);
   const size_t n4 = (size_t)rows * (size_t)(C / 4);
-  PN_DISPATCH_OP(operand_mode, (cast_operand_kernel<OP><<<grid_for(n4), 256, 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(
+  PN_DISPATCH_OP(operand_mode, (launch_kernel(cast_operand_kernel<OP>, dim3(grid_for(n4)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream_v), 1, 
       x, y, (size_t)rows, (int)C)));
   PN_CHECK_CUDA(cudaGetLastError());
   return PN_OK;
@@ -380,7 +393,7 @@ extern "C" int pn_geglu_operand(const float* in, void* y, int64_t rows, int64_t 
   PN_REQUIRE(in && y && rows > 0 && inner > 0 && inner % 16 == 0, "pn_geglu_operand: bad arguments");
   PN_REQUIRE(operand_mode >= 0 && operand_mode <= 2, "pn_geglu_operand: operand_mode %d", operand_mode);
   const size_t n4 = (size_t)rows * (size_t)(inner / 4);
-  PN_DISPATCH_OP(operand_mode, (geglu_operand_kernel<OP><<<grid_for(n4), 256, 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(
+  PN_DISPATCH_OP(operand_mode, (launch_kernel(geglu_operand_kernel<OP>, dim3(grid_for(n4)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream_v), 1, 
       in, y, (size_t)rows, (int)inner)));
   PN_CHECK_CUDA(cudaGetLastError());
   return PN_OK;
@@ -390,7 +403,7 @@ extern "C" int pn_timestep_embedding(const int64_t* t, float* out, int64_t n, in
                                      void* stream_v) {
   PN_REQUIRE(t && out && n > 0 && dim >= 2, "pn_timestep_embedding: bad arguments");
   const int total = (int)(n * (dim / 2));
-  timestep_embedding_kernel<<<(total + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(
+  launch_kernel(timestep_embedding_kernel, dim3((total + 255) / 256), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream_v), 1, 
       reinterpret_cast<const long long*>(t), out, (int)n, (int)dim, freqs);
   PN_CHECK_CUDA(cudaGetLastError());
   return PN_OK;
@@ -407,9 +420,9 @@ extern "C" int pn_linear_small(const float* x, const void* W_any, int w_is_f32, 
 #define PN_LS(TW)                                                                                                               \
   do {                                                                                                                          \
     const TW* W = reinterpret_cast<const TW*>(W_any);                                                                          \
-    if (M <= 8) linear_small_kernel<8, TW><<<blocks, 128, 0, st>>>(x, W, bias, y, (int)M, (int)N, (int)K, ldy, silu_in, silu_out);        \
-    else if (M <= 16) linear_small_kernel<16, TW><<<blocks, 128, 0, st>>>(x, W, bias, y, (int)M, (int)N, (int)K, ldy, silu_in, silu_out); \
-    else linear_small_kernel<32, TW><<<blocks, 128, 0, st>>>(x, W, bias, y, (int)M, (int)N, (int)K, ldy, silu_in, silu_out);              \
+    if (M <= 8) launch_kernel(linear_small_kernel<8, TW>, dim3(blocks), dim3(128), 0, st, 1, x, W, bias, y, (int)M, (int)N, (int)K, ldy, silu_in, silu_out);        \
+    else if (M <= 16) launch_kernel(linear_small_kernel<16, TW>, dim3(blocks), dim3(128), 0, st, 1, x, W, bias, y, (int)M, (int)N, (int)K, ldy, silu_in, silu_out); \
+    else launch_kernel(linear_small_kernel<32, TW>, dim3(blocks), dim3(128), 0, st, 1, x, W, bias, y, (int)M, (int)N, (int)K, ldy, silu_in, silu_out);              \
   } while (0)
   if (w_is_f32) PN_LS(float);
   else PN_LS(__nv_bfloat16);
@@ -424,7 +437,7 @@ extern "C" int pn_im2col3x3_s2(const float* x, void* out, int64_t frames, int64_
   PN_REQUIRE(operand_mode == PN_OP_BF16 || operand_mode == PN_OP_SPLIT3, "pn_im2col3x3_s2: operand_mode %d", operand_mode);
   const int Ho = (int)((H + 2 - 3) / 2 + 1), Wo = (int)((W + 2 - 3) / 2 + 1);
   const size_t total = (size_t)frames * Ho * Wo * 9 * (C / 8);
-  PN_DISPATCH_OP(operand_mode, (im2col_s2_kernel<OP><<<grid_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(
+  PN_DISPATCH_OP(operand_mode, (launch_kernel(im2col_s2_kernel<OP>, dim3(grid_for(total)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream_v), 1, 
       x, out, (int)frames, (int)H, (int)W, (int)C, Ho, Wo)));
   PN_CHECK_CUDA(cudaGetLastError());
   return PN_OK;
@@ -434,7 +447,7 @@ extern "C" int pn_cfg_euler_step(float* x, const float* net2, float* x_in_next, 
                                  float sigma_next, float cfg_scale, float c_in_next, int net_is_denoised,
                                  void* stream_v) {
   PN_REQUIRE(x && net2 && n > 0 && sigma > 0.f, "pn_cfg_euler_step: bad arguments");
-  cfg_euler_kernel<<<grid_for((size_t)n), 256, 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(
+  launch_kernel(cfg_euler_kernel, dim3(grid_for((size_t)n)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream_v), 1, 
       x, net2, x_in_next, (size_t)n, sigma, sigma_q, sigma_next, cfg_scale, c_in_next, net_is_denoised);
   PN_CHECK_CUDA(cudaGetLastError());
   return PN_OK;
@@ -442,7 +455,7 @@ extern "C" int pn_cfg_euler_step(float* x, const float* net2, float* x_in_next, 
 
 extern "C" int pn_scale_dup(const float* x, float* out, int64_t n, float s, int copies, void* stream_v) {
   PN_REQUIRE(x && out && n > 0 && copies >= 1, "pn_scale_dup: bad arguments");
-  scale_dup_kernel<<<grid_for((size_t)n), 256, 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(x, out, (size_t)n, s, copies);
+  launch_kernel(scale_dup_kernel, dim3(grid_for((size_t)n)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream_v), 1, x, out, (size_t)n, s, copies);
   PN_CHECK_CUDA(cudaGetLastError());
   return PN_OK;
 }
@@ -453,7 +466,7 @@ extern "C" int pn_fingerprint(const void* x, int64_t nbytes, uint64_t* out2, voi
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
   PN_CHECK_CUDA(cudaMemsetAsync(out2, 0, 16, st));
   const size_t nwords = (size_t)nbytes / 4;
-  fingerprint_kernel<<<grid_for(nwords), 256, 0, st>>>(reinterpret_cast<const uint32_t*>(x), nwords,
+  launch_kernel(fingerprint_kernel, dim3(grid_for(nwords)), dim3(256), 0, st, 1, reinterpret_cast<const uint32_t*>(x), nwords,
                                                       reinterpret_cast<unsigned long long*>(out2));
   PN_CHECK_CUDA(cudaGetLastError());
   return PN_OK;
@@ -468,7 +481,7 @@ extern "C" int pn_softmax_rows(const float* in, void* out_bf16, int64_t rows, in
   const size_t smem = (size_t)N * sizeof(float);
   const int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&softmax_rows_kernel), smem);
   if (rc != PN_OK) return rc;
-  softmax_rows_kernel<<<(unsigned)rows, 256, smem, reinterpret_cast<cudaStream_t>(stream_v)>>>(
+  launch_kernel(softmax_rows_kernel, dim3((unsigned)rows), dim3(256), smem, reinterpret_cast<cudaStream_t>(stream_v), 1, 
       in, reinterpret_cast<__nv_bfloat16*>(out_bf16), (int)N, ld_in, ld_out, scale * 1.4426950408889634f);
   PN_CHECK_CUDA(cudaGetLastError());
   return PN_OK;

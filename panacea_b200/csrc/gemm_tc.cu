@@ -205,6 +205,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_prologue_done();        // barriers / TMEM are set up: from here on global memory is touched
 
   // Producer and issuer loops are executed by all 32 lanes of their warp with the asynchronous instructions under an
   // elect.sync predicate: ptxas then emits the TMA / UMMA instructions straight from uniform registers. (Issued from
@@ -914,20 +915,8 @@ static int launch_gemm_mode(const GemmParams& p, cudaStream_t stream) {
   const int num_tiles = ((tiles_m + NCTA - 1) / NCTA) * p.tiles_col;
   int units = sm_count() / NCTA;
   if (units > num_tiles) units = num_tiles;
-  cudaLaunchConfig_t cfg;
-  std::memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(units * NCTA);
-  cfg.blockDim = dim3(gemm_threads(MODE));
-  cfg.dynamicSmemBytes = S::TOTAL;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = NCTA;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  PN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, NCTA, MODE>, p));
+  PN_CHECK_CUDA(launch_kernel(gemm_tc_kernel<BN, STAGES, NCTA, MODE>, dim3(units * NCTA), dim3(gemm_threads(MODE)), S::TOTAL, stream,
+                             NCTA, p));
   return PN_OK;
 }
 

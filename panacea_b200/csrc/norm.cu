@@ -199,6 +199,7 @@ template <int CPG, int OP>
 __global__ void __launch_bounds__(512) gn_pixel_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, void* __restrict__ y,
                                                        int T, int P, int C, float eps, int act_silu) {
+  pdl_prologue_done();
   __shared__ float red[16][32];
   const int t = threadIdx.x >> 5, g = threadIdx.x & 31;
   const int b = blockIdx.x / P, p = blockIdx.x - b * P;
@@ -260,6 +261,7 @@ template <int MAXV, int OP, typename TIn>
 __global__ void __launch_bounds__(256) layernorm_kernel(const TIn* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, void* __restrict__ y,
                                                         long long rows, int C, float eps) {
+  pdl_prologue_done();
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -410,7 +412,7 @@ extern "C" int pn_groupnorm_pixel_silu(const float* x, const float* gamma, const
   const int threads = (int)frames_per_seq * 32;
   const int T = (int)frames_per_seq, P = (int)pixels, C = (int)channels;
   switch (C / 32) {
-#define PN_GNP_CASE(CPG) case CPG: PN_DISPATCH_OP(operand_mode, (gn_pixel_kernel<CPG, OP><<<(unsigned)blocks, threads, 0, st>>>(x, gamma, beta, y, T, P, C, eps, act_silu))); break;
+#define PN_GNP_CASE(CPG) case CPG: PN_DISPATCH_OP(operand_mode, (launch_kernel(gn_pixel_kernel<CPG, OP>, dim3((unsigned)blocks), dim3(threads), 0, st, 1, x, gamma, beta, y, T, P, C, eps, act_silu))); break;
     PN_GNP_CASE(2) PN_GNP_CASE(4) PN_GNP_CASE(6) PN_GNP_CASE(8) PN_GNP_CASE(10) PN_GNP_CASE(12) PN_GNP_CASE(16) PN_GNP_CASE(20)
     PN_GNP_CASE(24) PN_GNP_CASE(30) PN_GNP_CASE(32) PN_GNP_CASE(40) PN_GNP_CASE(60) PN_GNP_CASE(80)
 #undef PN_GNP_CASE
@@ -434,10 +436,10 @@ extern "C" int pn_layernorm(const void* x, int x_is_bf16, const float* gamma, co
 #define PN_LN(MAXV)                                                                                                          \
   do {                                                                                                                      \
     if (x_is_bf16)                                                                                                          \
-      PN_DISPATCH_OP(operand_mode, (layernorm_kernel<MAXV, OP, __nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(             \
+      PN_DISPATCH_OP(operand_mode, (launch_kernel(layernorm_kernel<MAXV, OP, __nv_bfloat16>, dim3((unsigned)blocks), dim3(256), 0, st, 1,              \
                                        reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta, y, rows, C, eps)));           \
     else                                                                                                                    \
-      PN_DISPATCH_OP(operand_mode, (layernorm_kernel<MAXV, OP, float><<<(unsigned)blocks, 256, 0, st>>>(                     \
+      PN_DISPATCH_OP(operand_mode, (launch_kernel(layernorm_kernel<MAXV, OP, float>, dim3((unsigned)blocks), dim3(256), 0, st, 1,                      \
                                        reinterpret_cast<const float*>(x), gamma, beta, y, rows, C, eps)));                   \
   } while (0)
   if (C <= 512) PN_LN(4);

@@ -26,6 +26,17 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch: every kernel of the step is launched with programmatic stream serialization
+// (common.cuh::launch_kernel). `pdl_prologue_done()` lets the NEXT kernel's CTAs be scheduled as this kernel's CTAs
+// retire (its launch latency, barrier/TMEM set-up and the tail of this grid overlap) and then blocks until every
+// prerequisite grid has completed and flushed its memory; nothing before it may touch global memory.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_prologue_done() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -220,6 +231,14 @@ __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)
                "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -315,6 +334,16 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= 1ull << 46;  // descriptor version for Blackwell
   d |= 2ull << 61;  // SWIZZLE_128B
+  return d;
+}
+// 32B-swizzled tile whose rows are 32 bytes (16 bf16): layout type 6 = SWIZZLE_32B; 8-row groups are sbo_bytes apart.
+__device__ __forceinline__ uint64_t umma_smem_desc_sw32(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;
+  d |= 6ull << 61;  // SWIZZLE_32B
   return d;
 }
 // Same with an explicit base offset (bits [49,52)): needed when the tile does not start on a 1024-byte boundary of

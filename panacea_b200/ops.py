@@ -202,19 +202,19 @@ class NativeOps:
         return y
 
     # ------------------------------------------------------------------ attention
-    def _attention(self, q, k, v, out, *, q_ld, kv_ld, out_ld, F, H, V, W, Hk, Vk, Wk, kv_frame_div, heads, views):
+    def _attention(self, q, k, v, out, *, q_ld, kv_ld, out_ld, F, H, V, W, Hk, Vk, Wk, kv_frame_div, heads, views, head_dim=64):
         a = _lib.AttnArgs()
         a.q, a.k, a.v, a.out = q, k, v, out
         a.q_ld, a.kv_ld, a.out_ld = q_ld, kv_ld, out_ld
         a.F, a.H, a.V, a.W = F, H, V, W
         a.Hk, a.Vk, a.Wk = Hk, Vk, Wk
         a.kv_frame_div = kv_frame_div
-        a.heads, a.head_dim = heads, 64
+        a.heads, a.head_dim = heads, head_dim
         for vi, lst in enumerate(views):
             a.kv_view_count[vi] = len(lst)
             for j, kvv in enumerate(lst):
                 a.kv_views[vi][j] = kvv
-        a.scale = 64 ** -0.5
+        a.scale = head_dim ** -0.5
         _lib.check(self.lib.pn_attention(C.byref(a), _stream()), "pn_attention")
         self.launches += 1
 
@@ -224,12 +224,13 @@ class NativeOps:
         _req(qkv.is_cuda and qkv.dtype == BF16 and qkv.is_contiguous() and qkv.dim() == 5, "attention_view: qkv bf16 [F,H,V,w,3C]")
         Fr, H, V, w, C3 = qkv.shape
         Cc = C3 // 3
-        _req(Cc == heads * 64, "attention_view: head_dim must be 64")
+        d = Cc // heads
+        _req(Cc == heads * d and d in (64, 80), "attention_view: head_dim must be 64 or 80")
         out = torch.empty((Fr, H, V, w, Cc), device=qkv.device, dtype=BF16)
         views = [list(neighbours[v]) for v in range(V)] if cross else [[v] for v in range(V)]
         base = qkv.data_ptr()
         self._attention(base, base + 2 * Cc, base + 4 * Cc, out.data_ptr(), q_ld=C3, kv_ld=C3, out_ld=Cc, F=Fr, H=H, V=V, W=w,
-                        Hk=H, Vk=V, Wk=w, kv_frame_div=1, heads=heads, views=views)
+                        Hk=H, Vk=V, Wk=w, kv_frame_div=1, heads=heads, views=views, head_dim=d)
         return out
 
     def attention_text(self, q, kv, heads):
@@ -237,11 +238,13 @@ class NativeOps:
         _req(q.is_cuda and q.dtype == BF16 and q.is_contiguous() and kv.dtype == BF16 and kv.is_contiguous(), "attention_text: bf16 contiguous")
         b, Nq, Cc = q.shape
         Nk = kv.shape[1]
-        _req(kv.shape[0] == b and kv.shape[2] == 2 * Cc and Cc == heads * 64 and Nk <= 128, "attention_text: bad shapes")
+        d = Cc // heads
+        _req(kv.shape[0] == b and kv.shape[2] == 2 * Cc and Cc == heads * d and d in (64, 80) and Nk <= (128 if d == 64 else 112),
+             "attention_text: bad shapes")
         out = torch.empty_like(q)
         base = kv.data_ptr()
         self._attention(q.data_ptr(), base, base + 2 * Cc, out.data_ptr(), q_ld=Cc, kv_ld=2 * Cc, out_ld=Cc, F=b, H=1, V=1,
-                        W=Nq, Hk=1, Vk=1, Wk=Nk, kv_frame_div=1, heads=heads, views=[[0]])
+                        W=Nq, Hk=1, Vk=1, Wk=Nk, kv_frame_div=1, heads=heads, views=[[0]], head_dim=d)
         return out
 
     def attention_temporal(self, qkv, heads):
@@ -249,11 +252,12 @@ class NativeOps:
         _req(qkv.is_cuda and qkv.dtype == BF16 and qkv.is_contiguous() and qkv.dim() == 4, "attention_temporal: qkv bf16 [b,T,P,3C]")
         b, T, P, C3 = qkv.shape
         Cc = C3 // 3
-        _req(Cc == heads * 64, "attention_temporal: head_dim must be 64")
+        d = Cc // heads
+        _req(Cc == heads * d and d in (64, 80), "attention_temporal: head_dim must be 64 or 80")
         out = torch.empty((b, T, P, Cc), device=qkv.device, dtype=BF16)
         base = qkv.data_ptr()
-        _lib.check(self.lib.pn_attention_temporal(base, base + 2 * Cc, base + 4 * Cc, out.data_ptr(), b, T, P, heads, 64, C3, Cc,
-                                                 64 ** -0.5, _stream()), "pn_attention_temporal")
+        _lib.check(self.lib.pn_attention_temporal(base, base + 2 * Cc, base + 4 * Cc, out.data_ptr(), b, T, P, heads, d, C3, Cc,
+                                                 d ** -0.5, _stream()), "pn_attention_temporal")
         self.launches += 1
         return out
 

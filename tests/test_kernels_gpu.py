@@ -80,11 +80,13 @@ def _view_ref(qkv, heads, cross):
     q, k, v = qkv.float().split(C, dim=-1)
     out = torch.empty_like(q)
 
+    d = C // heads
+
     def mha(qi, ki, vi):
         B, Nq, _ = qi.shape
-        qh = qi.reshape(B, Nq, heads, 64).transpose(1, 2)
-        kh = ki.reshape(B, -1, heads, 64).transpose(1, 2)
-        vh = vi.reshape(B, -1, heads, 64).transpose(1, 2)
+        qh = qi.reshape(B, Nq, heads, d).transpose(1, 2)
+        kh = ki.reshape(B, -1, heads, d).transpose(1, 2)
+        vh = vi.reshape(B, -1, heads, d).transpose(1, 2)
         return F.scaled_dot_product_attention(qh, kh, vh).transpose(1, 2).reshape(B, Nq, C)
 
     for i in range(V):
@@ -104,6 +106,32 @@ def test_attention_view(ops, Fr, H, w, heads, cross):
     out = ops.attention_view(qkv, heads, cross, NEIGH)
     torch.cuda.synchronize()
     _close(out, _view_ref(qkv, heads, cross), 2e-2, f"attention_view cross={cross}")
+
+
+@pytest.mark.parametrize("Fr,H,w,heads", [(1, 32, 56, 4), (2, 16, 28, 2), (2, 8, 14, 3), (1, 32, 64, 2), (2, 2, 3, 1), (2, 16, 24, 2)])
+@pytest.mark.parametrize("cross", [False, True])
+def test_attention_view_head_dim_80(ops, Fr, H, w, heads, cross):
+    """BASELINE.json configs[4]: head_dim 80 = a 64-channel tile + a 16-channel tile per Q/K/V (fifth K step of S, second
+    N = 16 MMA of P V), incl. the headline 32x56 views and the native 32x64 views (64-key blocks there)."""
+    C = heads * 80
+    qkv = _rand((Fr, H, 6, w, 3 * C), 18, 1.0, torch.bfloat16)
+    out = ops.attention_view(qkv, heads, cross, NEIGH)
+    torch.cuda.synchronize()
+    _close(out, _view_ref(qkv, heads, cross), 2e-2, f"attention_view d=80 cross={cross}")
+
+
+def test_attention_text_head_dim_80(ops):
+    b, Nq, heads, Nk = 2, 700, 2, 77
+    C = heads * 80
+    q = _rand((b, Nq, C), 19, 1.0, torch.bfloat16)
+    kv = _rand((b, Nk, 2 * C), 20, 1.0, torch.bfloat16)
+    out = ops.attention_text(q, kv, heads)
+    torch.cuda.synchronize()
+    qh = q.float().reshape(b, Nq, heads, 80).transpose(1, 2)
+    kh = kv.float()[..., :C].reshape(b, Nk, heads, 80).transpose(1, 2)
+    vh = kv.float()[..., C:].reshape(b, Nk, heads, 80).transpose(1, 2)
+    ref = F.scaled_dot_product_attention(qh, kh, vh).transpose(1, 2).reshape(b, Nq, C)
+    _close(out, ref, 2e-2, "attention_text d=80")
 
 
 def test_attention_view_sharp_softmax(ops):
@@ -130,17 +158,18 @@ def test_attention_text(ops, b, Nq, heads, Nk):
     _close(out, ref, 2e-2, "attention_text")
 
 
+@pytest.mark.parametrize("d", [64, 80])
 @pytest.mark.parametrize("b,T,P,heads", [(2, 8, 100, 2), (1, 8, 2688, 5), (2, 4, 33, 1), (1, 16, 64, 2), (1, 1, 10, 1), (1, 5, 40, 2),
                                            (2, 12, 17, 1)])
-def test_attention_temporal(ops, b, T, P, heads):
-    C = heads * 64
+def test_attention_temporal(ops, b, T, P, heads, d):
+    C = heads * d
     qkv = _rand((b, T, P, 3 * C), 14, 1.0, torch.bfloat16)
     out = ops.attention_temporal(qkv, heads)
     torch.cuda.synchronize()
     q, k, v = qkv.float().split(C, dim=-1)
 
-    def hs(z):  # [b,T,P,C] -> [b*P, heads, T, 64]
-        return z.permute(0, 2, 1, 3).reshape(b * P, T, heads, 64).transpose(1, 2)
+    def hs(z):  # [b,T,P,C] -> [b*P, heads, T, d]
+        return z.permute(0, 2, 1, 3).reshape(b * P, T, heads, d).transpose(1, 2)
 
     ref = F.scaled_dot_product_attention(hs(q), hs(k), hs(v)).transpose(1, 2).reshape(b, P, T, C).permute(0, 2, 1, 3)
     _close(out, ref, 2e-2, "attention_temporal")

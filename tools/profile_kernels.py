@@ -32,6 +32,9 @@ def main():
     wc2 = (torch.randn(1280, 9 * 1280, device=dev) * (9 * 1280) ** -0.5).to(BF16)
     b2 = torch.randn(1280, device=dev)
     g = torch.ones(C, device=dev); bz = torch.zeros(C, device=dev)
+    xb = torch.randn(M, C, device=dev).to(BF16)
+    w3 = (torch.randn(3 * C, C, device=dev) * C ** -0.5).to(BF16)
+    kvt = torch.randn(2, 77, 2 * C, device=dev).to(BF16)
 
     def run_all():
         ops.gemm(x.view(BT, H, W, C), wc, bias=bias, taps=(3, 3))                       # conv3x3 level 0
@@ -43,6 +46,13 @@ def main():
         ops.attention_view(qkv, 5, True, NEIGH)                                        # cross-view attention
         ops.groupnorm(res.view(BT, H * W, C), g, bz, 1e-5, True)
         ops.layernorm(res, g, bz)
+        ops.layernorm(xb, g, bz)                                                       # bf16 token stream LayerNorm
+        ops.gemm(x, w, bias=bias, residual=xb, out=xb, out_dtype=BF16)                 # attn out-proj + bf16 residual (streaming)
+        ops.gemm(x, w3, out_dtype=BF16)                                                # qkv projection (bf16 streaming)
+        ops.gemm(h4, w4, bias=bias, residual=xb, out_dtype=BF16)                       # ff2 + bf16 residual, operand emit
+        ops.attention_temporal(qkv.view(2, 8, H * W, 3 * C), 5)                        # temporal attention T=8
+        ops.attention_text(xb.view(2, 8 * H * W, C), kvt, 5)                           # text cross-attention (77 keys)
+        ops.groupnorm_pixel(res.view(2, 8, H * W, C), g, bz, 1e-5, True)               # pixel-wise temporal GroupNorm
 
     for _ in range(2):
         run_all()
