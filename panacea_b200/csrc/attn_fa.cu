@@ -384,6 +384,11 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
         const bool need = (j > 0) && __any_sync(0xffffffffu, upd);
         const f32x2 nm2 = f2_splat(-m_run);
         f32x2 rs2[2] = {0ull, 0ull};
+        // Per-block rendezvous of the two groups. ptxas sees no dependence between MUFU.EX2 and BAR.SYNC and schedules the
+        // exponentials AHEAD of this barrier, so what the pair of named barriers really does is keep the two groups within
+        // one block of each other (measured: 550 us with it, 637 us free-running at level 0). Forcing the exponentials
+        // behind the barrier (a true alternation of the exp2 phases, r02 experiment) serialises the groups' non-MUFU work
+        // with each other's exponentials and is slower (611 us).
         if (turns) named_bar_sync(1 + sl, 256);
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) {

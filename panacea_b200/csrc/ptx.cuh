@@ -216,6 +216,11 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
       : "memory");
 }
 
+__device__ __forceinline__ float ld_shared_volatile_f32(const float* p) {
+  float v;
+  asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
 // named barriers (ids 1..15; id 0 is __syncthreads): producer/consumer hand-off between warp groups
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
