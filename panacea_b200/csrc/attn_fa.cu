@@ -51,12 +51,6 @@ struct FaL {
   static constexpr uint32_t S_STRIDE = D == 64 ? 128 : 112, P_BASE = D == 64 ? 256 : 224, P_STRIDE = D == 64 ? 64 : 56;
   static constexpr uint32_t O_BASE = D == 64 ? 384 : 336, O_STRIDE = D;
 };
-// PN_ATTN_DEBUG timing experiments exist only in diagnostics builds (-DPN_GEMM_ROLE_TIMERS, see build.py)
-#ifdef PN_GEMM_ROLE_TIMERS
-constexpr bool kFaExperiments = true;
-#else
-constexpr bool kFaExperiments = false;
-#endif
 constexpr float FA_LAZY_LOG2 = 8.0f;              // raise the reference maximum only when it grew by more than 2^8
 
 struct FaParams {
@@ -74,8 +68,9 @@ struct FaParams {
   int kv_frame_div;            // kv frame = q frame / kv_frame_div
   int total_items;
   float scale_log2;            // softmax scale * log2(e)
-  int debug;                   // PN_ATTN_DEBUG (timing experiments): 1 = no softmax math, 2 = no MMA issue,
-                               // 4 = no exp2-phase turn taking between the two softmax groups
+#ifdef PN_GEMM_ROLE_TIMERS
+  int debug;                   // diagnostics builds only — PN_ATTN_DEBUG: 1 = no softmax math, 2 = no MMA issue, 4 = no rendezvous
+#endif
   __nv_bfloat16* out;
   long long out_ld;            // token stride of out (elements)
 };
@@ -126,7 +121,11 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int dbgmode = kFaExperiments ? p.debug : 0;
+#ifdef PN_GEMM_ROLE_TIMERS
+  const int dbgmode = p.debug;
+#else
+  constexpr int dbgmode = 0;
+#endif
 
   // zero Q/K/V staging once: rows a TMA box does not cover (kv_rows..kv_n) must read as 0, never as stale NaNs
   {
@@ -532,11 +531,13 @@ extern "C" int pn_attention(const pn_attn_args* a, void* stream_v) {
   }
   p.kv_frame_div = a->kv_frame_div;
   p.scale_log2 = a->scale * 1.4426950408889634f;
+#ifdef PN_GEMM_ROLE_TIMERS
   {
     static int dbg = -1;
     if (dbg < 0) { const char* e = std::getenv("PN_ATTN_DEBUG"); dbg = e ? std::atoi(e) : 0; }
     p.debug = dbg;
   }
+#endif
   p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
   p.out_ld = a->out_ld;
 

@@ -36,9 +36,10 @@ struct GemmParams {
   CUtensorMap mapOut;          // MODE 4 only: fp32 output / residual, box {32 floats, 128 rows}
   CUtensorMap mapRes;
   int has_res;
-  int halo_base_offset;        // MODE 6: encode (start >> 7) & 7 in the A descriptors (experiment switch)
-  int debug;                   // PN_GEMM_DEBUG (timing experiments): 1 = no TMA loads after the first ring fill, 2 = no MMA issue,
-                               // 3 = epilogue reads TMEM only, 4 = no global stores
+#ifdef PN_GEMM_ROLE_TIMERS
+  int debug;                   // diagnostics builds only — PN_GEMM_DEBUG timing experiments: 1 = no TMA loads after the first
+                               // ring fill, 2 = no MMA issue, 3 = epilogue reads TMEM only, 4 = no global stores, 5 = role timers
+#endif
   // geometry of the A tensor / output rows
   int NB, H, W;
   int tw, th, tn;             // tile box extents, tw*th*tn == 128
@@ -101,10 +102,8 @@ constexpr bool kRoleTimers = true;
 #else
 constexpr bool kRoleTimers = false;
 #endif
-// The PN_GEMM_DEBUG timing experiments (1-5) cost a constant-bank load, a compare and a branch per k-block in the two
-// single-warp loops that pace the short-K GEMMs: they exist only in diagnostics builds
-// (PN_GEMM_ROLE_TIMERS=1 python -m panacea_b200.build --force); the product build folds them away.
-constexpr bool kExperiments = kRoleTimers;
+// The PN_GEMM_DEBUG timing experiments (1-5) exist only in diagnostics builds
+// (PN_GEMM_ROLE_TIMERS=1 python -m panacea_b200.build --force); in the product build `dbgmode` is the constant 0.
 
 template <int BN, int STAGES, int NCTA, int MODE>
 __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
@@ -130,7 +129,11 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int dbgmode = kExperiments ? p.debug : 0;
+#ifdef PN_GEMM_ROLE_TIMERS
+  const int dbgmode = p.debug;
+#else
+  constexpr int dbgmode = 0;
+#endif
   // NCTA == 2: the two CTAs of a cluster form a UMMA pair (cta_group::2). Each CTA owns 128 rows of a 256-row
   // tile (its own A stage and TMEM lanes) and stages half of the N tile's weight rows; the leader (rank 0)
   // issues the MMAs for both, and the weights cross the L2->SM fabric once per pair instead of once per CTA.
@@ -860,6 +863,7 @@ static int gemm_force_bn() {      // PN_GEMM_BN: force the N tile of the non-str
   return m;
 }
 
+#ifdef PN_GEMM_ROLE_TIMERS
 static int gemm_debug_mode() {
   static int m = -1;
   if (m < 0) {
@@ -868,9 +872,11 @@ static int gemm_debug_mode() {
   }
   return m;
 }
+#endif
 
-static int conv_halo_mode() {     // PN_CONV_HALO: 0 = off, 2 = on, descriptor base_offset 0 (default; verified on B200: the
-                                   // 128B swizzle is a function of the absolute smem address), 1 = on with (start>>7)&7 (wrong)
+static int conv_halo_mode() {     // PN_CONV_HALO=0 disables the haloed 3x3 conv (A/B measurements); the row-shifted A views use
+                                   // descriptor base_offset 0 (verified on B200: the 128B swizzle is a function of the absolute
+                                   // shared-memory address)
   static int m = -1;
   if (m < 0) {
     const char* e = getenv("PN_CONV_HALO");
@@ -975,7 +981,9 @@ extern "C" int pn_gemm(const pn_gemm_args* a, void* stream_v) {
   p.N = a->N;
   p.out = a->out; p.bias = a->bias; p.rowvec = a->rowvec; p.residual = reinterpret_cast<const float*>(a->residual);
   p.residual2 = a->residual2;
+#ifdef PN_GEMM_ROLE_TIMERS
   p.debug = gemm_debug_mode();
+#endif
   p.ldo = a->ldo; p.ldr = a->ldr; p.ldr2 = a->ldr2;
   p.ldv = a->rowvec_ld > 0 ? a->rowvec_ld : a->N;
   p.rows_per_group = a->rows_per_group > 0 ? a->rows_per_group : 1;
@@ -1006,7 +1014,6 @@ extern "C" int pn_gemm(const pn_gemm_args* a, void* stream_v) {
     BN = 160;
     const long long tiles_m_h = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
     NCTA = (tiles_m_h * (a->N / 160) >= 2 * sm_count() || force == 2) ? 2 : 1;
-    p.halo_base_offset = conv_halo_mode() == 1 ? 1 : 0;
   }
   // Streaming epilogue (MODE 4): fp32 output whose tile rows are consecutive output rows, short K loop (HBM-bound).
   const long long k_total = (long long)a->taps_h * a->taps_w * a->C;
