@@ -73,9 +73,21 @@ typedef struct pn_gemm_args {
   int32_t out_bf16;
   int32_t geglu;
   int32_t residual_bf16;  /* the residual is bf16 (bf16 output only): the transformer blocks' bf16 token stream */
+  /* LayerNorm folded into the GEMMs around the bf16 token stream (attention.py:699-701 + :726-747, norm1/2/3):
+   * ln_stats_out — this GEMM (1x1, K <= 640, bf16 out) also writes, per output row, pn_gemm_ln_parts(N) partial
+   *   (sum, sum of squares) pairs of the bf16 values it stores: float [rows][parts][2];
+   * ln_stats_in / ln_parts_in / ln_colsum / ln_eps — A is the UN-normalised stream, B = W diag(gamma); the epilogue
+   *   finishes the LayerNorm: out = rstd_m (acc - mean_m s_n) + bias_n with s_n = ln_colsum[n] = sum_k B[n,k] and the
+   *   caller's bias_n = sum_k beta_k W[n,k] (+ the layer's own bias); mean/rstd over the C = K channels of row m. */
+  const float* ln_stats_in;
+  const float* ln_colsum;
+  float* ln_stats_out;
+  int32_t ln_parts_in;
+  float ln_eps;
 } pn_gemm_args;
 
 int pn_gemm(const pn_gemm_args* args, void* stream);
+int pn_gemm_ln_parts(int N);
 
 /* ------------------------------------------------------------------------------------------------
  * pn_attention — tcgen05 flash attention over view-tiled tokens (head_dim 64).

@@ -28,6 +28,8 @@ class GemmArgs(C.Structure):
         ("N", C.c_int32), ("taps_h", C.c_int32), ("taps_w", C.c_int32),
         ("rows_per_group", C.c_int32), ("n_groups", C.c_int32),
         ("out_bf16", C.c_int32), ("geglu", C.c_int32), ("residual_bf16", C.c_int32),
+        ("ln_stats_in", C.c_void_p), ("ln_colsum", C.c_void_p), ("ln_stats_out", C.c_void_p),
+        ("ln_parts_in", C.c_int32), ("ln_eps", C.c_float),
     ]
 
 
@@ -51,6 +53,7 @@ SIGNATURES: dict[str, tuple] = {
     "pn_last_error": (C.c_char_p, []),
     "pn_abi_version": (C.c_int, []),
     "pn_gemm": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
+    "pn_gemm_ln_parts": (C.c_int, [C.c_int]),
     "pn_attention": (C.c_int, [C.POINTER(AttnArgs), _vp]),
     "pn_attention_temporal": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _i64, _i64, _f32, _vp]),
     "pn_attention_f32": (C.c_int, [C.POINTER(AttnArgs), C.c_int, _vp]),

@@ -55,6 +55,17 @@ struct GemmParams {
   const float* residual2;
   long long ldo, ldr, ldr2, ldv;
   int rows_per_group, n_groups;
+  // LayerNorm folded into the GEMMs around the bf16 token stream (attention.py:726-747: x + attn(norm(x))):
+  //  * a PRODUCER of the stream (MODE 5) also emits per-row partial sums (sum, sum of squares) of the bf16 values it
+  //    stores: ln_stats_out[row][tile_col * 2 + half][2] (ln_parts_out = 2 * tiles_col);
+  //  * a CONSUMER (MODE 5 or 2) multiplies the UN-normalised stream by W' = W diag(gamma) and finishes the LayerNorm in
+  //    its epilogue: out = rstd_m * (acc - mean_m * s_n) + t_n, s_n = sum_k W'[n,k], t_n = sum_k beta_k W[n,k] (+ bias,
+  //    passed as `bias`), mean/rstd from the ln_parts_in partial sums of row m.
+  const float* ln_stats_in;
+  const float* ln_colsum;
+  float* ln_stats_out;
+  int ln_parts_in, ln_parts_out;
+  float ln_inv_dim, ln_eps;
   int out_bf16;
   int res_bf16;                // the residual is bf16 (bf16 token stream of the transformer blocks), bf16 output only
   int geglu;
@@ -76,7 +87,7 @@ struct GemmSmem {
   static constexpr int RING_BYTES = MODE == 6 ? HALO_STAGES * A_HALO_BYTES + STAGES * B_BYTES : STAGES * STAGE_BYTES;
   static constexpr int STAGING_BYTES = gemm_streaming(MODE) ? (BN / 32) * RCHUNK_BYTES : NEPI * STAGE_WARP_BYTES;
   static constexpr bool BIAS_SMEM = (MODE == 1 || MODE == 2);    // the ALU-bound epilogues stage their bias slice in smem
-  static constexpr int ROWMAP_BYTES = gemm_streaming(MODE) ? 0 : NEPI * 32 * 4 + (BIAS_SMEM ? NEPI * 512 : 0);
+  static constexpr int ROWMAP_BYTES = gemm_streaming(MODE) ? 0 : NEPI * 32 * 4 + (BIAS_SMEM ? NEPI * 512 : 0) + (MODE == 2 ? NEPI * 512 : 0);
   static constexpr int BAR_BYTES = (2 * STAGES + 4 + 2 * (BN / 32) + 8) * 8 + 16;
   static constexpr int TOTAL = RING_BYTES + STAGING_BYTES + ROWMAP_BYTES + BAR_BYTES + 1024;
 };
@@ -516,6 +527,16 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
       const int thi = tm % p.tiles_h; tm /= p.tiles_h;
       const long long grow = (long long)(tm * p.H + thi) * p.W + twi * p.tw + r;
       const int n_base = tcol * BN;
+      const bool row_ok = grow < (long long)p.NB * p.H * p.W;
+      float ln_mu = 0.f, ln_rstd = 1.f;
+      if (MODE == 5 && p.ln_stats_in != nullptr && row_ok) {      // finish the LayerNorm statistics of this thread's row
+        float sm = 0.f, sq = 0.f;
+        const float2* st = reinterpret_cast<const float2*>(p.ln_stats_in) + grow * p.ln_parts_in;
+        for (int q = 0; q < p.ln_parts_in; ++q) { const float2 t2 = __ldg(st + q); sm += t2.x; sq += t2.y; }
+        ln_mu = sm * p.ln_inv_dim;
+        ln_rstd = rsqrtf(fmaxf(sq * p.ln_inv_dim - ln_mu * ln_mu, 0.f) + p.ln_eps);
+      }
+      float st_sum = 0.f, st_sq = 0.f;                            // partial row sums of what this thread stores (producer)
       { const long long w0 = dbg ? clock64() : 0; mbar_wait(&tmem_full[acc], acc_phase); if (dbg) d_tf += clock64() - w0; }
       tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t(lane_grp * 32) << 16) + acc * BN;
@@ -538,6 +559,14 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (MODE == 5 && p.ln_stats_in != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + n0 + j));
+              f[j] = ln_rstd * fmaf(-ln_mu, s4.x, f[j]); f[j + 1] = ln_rstd * fmaf(-ln_mu, s4.y, f[j + 1]);
+              f[j + 2] = ln_rstd * fmaf(-ln_mu, s4.z, f[j + 2]); f[j + 3] = ln_rstd * fmaf(-ln_mu, s4.w, f[j + 3]);
+            }
+          }
           if (p.bias != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -570,8 +599,18 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
                   f[8 * j + 2 * e] += t.x; f[8 * j + 2 * e + 1] += t.y;
                 }
               }
-              *q = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                              pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+              const uint4 o4 = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                                          pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+              *q = o4;
+              if (p.ln_stats_out != nullptr) {           // sums of the ROUNDED values: what the consumer's MMA will read
+                const uint32_t w4[4] = {o4.x, o4.y, o4.z, o4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float lo = __uint_as_float(w4[e] << 16), hi = __uint_as_float(w4[e] & 0xffff0000u);
+                  st_sum += lo + hi;
+                  st_sq = fmaf(lo, lo, fmaf(hi, hi, st_sq));
+                }
+              }
             }
           } else {
             uint8_t* rowp = staging + c * S::RCHUNK_BYTES + r * 128;
@@ -591,6 +630,8 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
           if (lane == 0) mbar_arrive(&c_ready[c]);
         }
       }
+      if (MODE == 5 && p.ln_stats_out != nullptr && row_ok)
+        reinterpret_cast<float2*>(p.ln_stats_out)[grow * p.ln_parts_out + tcol * 2 + half] = make_float2(st_sum, st_sq);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (dbg && lane == 0) {
@@ -607,6 +648,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
     uint8_t* my_stage = staging + ew * S::STAGE_WARP_BYTES;
     int* my_rowmap = rowmap + ew * 32;
     float* my_bias = reinterpret_cast<float*>(rowmap + NEPI * 32) + ew * 128;   // bias of this warp's <= 4 chunks
+    float* my_colsum = reinterpret_cast<float*>(rowmap + NEPI * 32) + NEPI * 128 + ew * 128;   // MODE 2: folded-LayerNorm s_n
     constexpr int NCH = BN / 32;
     constexpr int MYCH = (NCH + EG - 1) / EG;
     constexpr int PRECH = MYCH < 2 ? MYCH : 2;   // chunks whose residual is prefetched at tile start (register budget:
@@ -645,8 +687,23 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
           my_bias[k * 32 + lane] = (half + EG * k < NCH && n < p.N) ? __ldg(p.bias + n) : 0.f;
         }
       }
+      if (MODE == 2 && p.ln_stats_in != nullptr) {
+#pragma unroll
+        for (int k = 0; k < MYCH; ++k) {
+          const int n = n_base + (half + EG * k) * 32 + lane;
+          my_colsum[k * 32 + lane] = (half + EG * k < NCH && n < p.N) ? __ldg(p.ln_colsum + n) : 0.f;
+        }
+      }
       __syncwarp();
       const int my_row = my_rowmap[lane];
+      float ln_mu = 0.f, ln_rstd = 1.f;
+      if (MODE == 2 && p.ln_stats_in != nullptr && my_row >= 0) {
+        float sm = 0.f, sq = 0.f;
+        const float2* st = reinterpret_cast<const float2*>(p.ln_stats_in) + (long long)my_row * p.ln_parts_in;
+        for (int q = 0; q < p.ln_parts_in; ++q) { const float2 t2 = __ldg(st + q); sm += t2.x; sq += t2.y; }
+        ln_mu = sm * p.ln_inv_dim;
+        ln_rstd = rsqrtf(fmaxf(sq * p.ln_inv_dim - ln_mu * ln_mu, 0.f) + p.ln_eps);
+      }
       // ---- residual prefetch (fp32 output path): lane -> (row i*4 + lane/8, 16-byte column chunk lane%8)
       float4 rpre[PRECH][8];
       const bool pre = (MODE == 0 || MODE == 3) && (p.residual != nullptr);
@@ -689,6 +746,15 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (MODE == 2 && p.ln_stats_in != nullptr) {
+            const f32x2 nmu = f2_splat(-ln_mu), rs = f2_splat(ln_rstd);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 s4 = *reinterpret_cast<const float4*>(my_colsum + k * 32 + j);
+              f2_unpack(f2_mul(rs, f2_fma(nmu, f2_pack(s4.x, s4.y), f2_pack(f[j], f[j + 1]))), f[j], f[j + 1]);
+              f2_unpack(f2_mul(rs, f2_fma(nmu, f2_pack(s4.z, s4.w), f2_pack(f[j + 2], f[j + 3]))), f[j + 2], f[j + 3]);
+            }
+          }
           if (p.bias != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -929,7 +995,7 @@ static int launch_gemm_mode(const GemmParams& p, cudaStream_t stream) {
 template <int BN, int STAGES, int NCTA>
 static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
   // GEGLU runs 16 epilogue warps (its epilogue, not the k loop, is the long pole): one ring stage pays for their staging
-  if (p.geglu) return launch_gemm_mode<BN, (STAGES > 5 ? STAGES - 1 : STAGES), NCTA, 2>(p, stream);
+  if (p.geglu) return launch_gemm_mode<BN, (STAGES > 4 ? STAGES - 1 : STAGES), NCTA, 2>(p, stream);
   if (p.out_bf16) return launch_gemm_mode<BN, STAGES, NCTA, 1>(p, stream);
   if (p.residual2 != nullptr) return launch_gemm_mode<BN, STAGES, NCTA, 3>(p, stream);
   return launch_gemm_mode<BN, STAGES, NCTA, 0>(p, stream);
@@ -959,6 +1025,8 @@ extern "C" int pn_gemm(const pn_gemm_args* a, void* stream_v) {
                                    "pn_gemm: a bf16 residual needs bf16 output, no GEGLU, no second residual, ldr%%8==0");
   if (a->residual2) PN_REQUIRE(!a->out_bf16 && !a->geglu && a->ldr2 >= a->N && a->ldr2 % 4 == 0, "pn_gemm: residual2 needs fp32 out and a valid ldr2");
   if (a->rowvec) PN_REQUIRE(a->rows_per_group > 0 && a->n_groups > 0, "pn_gemm: rowvec needs rows_per_group/n_groups");
+  if (a->ln_stats_in) PN_REQUIRE(a->ln_colsum && a->ln_parts_in > 0 && a->ln_parts_in <= 64 && a->out_bf16 && a->taps_h == 1 && a->taps_w == 1,
+                                 "pn_gemm: a folded LayerNorm needs ln_colsum, 1..64 partial sums per row, a 1x1 GEMM and bf16 output");
 
   GemmParams p;
   std::memset(&p, 0, sizeof(p));
@@ -989,6 +1057,8 @@ extern "C" int pn_gemm(const pn_gemm_args* a, void* stream_v) {
   p.rows_per_group = a->rows_per_group > 0 ? a->rows_per_group : 1;
   p.n_groups = a->n_groups > 0 ? a->n_groups : 1;
   p.out_bf16 = a->out_bf16; p.geglu = a->geglu; p.res_bf16 = a->residual_bf16;
+  p.ln_stats_in = a->ln_stats_in; p.ln_colsum = a->ln_colsum; p.ln_stats_out = a->ln_stats_out;
+  p.ln_parts_in = a->ln_parts_in; p.ln_eps = a->ln_eps; p.ln_inv_dim = 1.0f / (float)a->C;
 
   // Tile selection. Big problems run on CTA pairs (cta_group::2, 256 x BN tiles: the weight tile is fetched once per
   // pair, which is what lifts the L2->SM-bound K loop); small ones keep single-CTA 128 x BN tiles for parallelism.
@@ -1052,6 +1122,11 @@ extern "C" int pn_gemm(const pn_gemm_args* a, void* stream_v) {
     }
   }
   p.tiles_col = (a->N + BN - 1) / BN;
+  if (a->ln_stats_out) {
+    PN_REQUIRE(stream_mode && a->out_bf16, "pn_gemm: ln_stats_out needs the streaming bf16 epilogue (1x1 GEMM, K <= 640, bf16 out, N %% 160 or 128 == 0)");
+    p.ln_parts_out = 2 * p.tiles_col;
+  }
+  if (a->ln_stats_in) PN_REQUIRE(a->geglu || (stream_mode && a->out_bf16), "pn_gemm: a folded LayerNorm needs the GEGLU or the streaming bf16 epilogue");
   // weight-stationary schedule: 1x1 GEMMs with K = 320 (5 k-blocks, every ring has >= 5 stages) and enough column
   // tiles and row tiles for the saved weight traffic to matter
   p.bstat = (gemm_bstat_enabled() && !halo_mode && a->taps_h == 1 && a->taps_w == 1 && a->C == 5 * BK && p.tiles_col >= 3 &&
@@ -1096,4 +1171,12 @@ extern "C" int pn_debug_gemm_counters(unsigned long long* out16) {
   PN_CHECK_CUDA(cudaDeviceSynchronize());
   PN_CHECK_CUDA(cudaMemcpyFromSymbol(out16, pn::g_gemm_dbg, sizeof(unsigned long long) * 16));
   return PN_OK;
+}
+
+// number of partial (sum, sum of squares) pairs per row that a streaming bf16 pn_gemm with N output columns writes to
+// ln_stats_out (2 per 160- or 128-wide column tile)
+extern "C" int pn_gemm_ln_parts(int N) {
+  if (N <= 0 || (N % 160 != 0 && N % 128 != 0)) return 0;
+  const int BN = (N % 160 == 0) ? 160 : 128;
+  return 2 * (N / BN);
 }

@@ -112,16 +112,28 @@ class Engine:
                     t = f"{k}.transformer_blocks{br}.0"
                     for nm in ("norm1", "norm2", "norm3"):
                         W[f"{t}.{nm}.g"] = f(P[f"{t}.{nm}.weight"]); W[f"{t}.{nm}.b"] = f(P[f"{t}.{nm}.bias"])
-                    W[t + ".qkv.w"] = mat(torch.cat([P[f"{t}.attn1.to_{n}.weight"].detach() for n in "qkv"], 0))
-                    W[t + ".q2.w"] = mat(P[t + ".attn2.to_q.weight"])
+                    fold = self._fold_ln(c)
+                    W[t + ".fold"] = fold
+                    wqkv = torch.cat([P[f"{t}.attn1.to_{n}.weight"].detach() for n in "qkv"], 0)
+                    if fold:   # LayerNorm folded into the consumer GEMM: W' = W diag(gamma), s = rowsum(bf16 W'), t = W beta
+                        W[t + ".qkv.w"], W[t + ".qkv.s"], W[t + ".qkv.t"] = self._ln_fold_pack(wqkv, None, W[t + ".norm1.g"], W[t + ".norm1.b"])
+                        W[t + ".q2.w"], W[t + ".q2.s"], W[t + ".q2.t"] = self._ln_fold_pack(
+                            P[t + ".attn2.to_q.weight"].detach(), None, W[t + ".norm2.g"], W[t + ".norm2.b"])
+                    else:
+                        W[t + ".qkv.w"] = mat(wqkv)
+                        W[t + ".q2.w"] = mat(P[t + ".attn2.to_q.weight"])
                     W[t + ".kv2.w"] = mat(torch.cat([P[t + ".attn2.to_k.weight"].detach(), P[t + ".attn2.to_v.weight"].detach()], 0))
                     for a in ("attn1", "attn2"):
                         W[f"{t}.{a}.o.w"] = mat(P[f"{t}.{a}.to_out.0.weight"])
                         W[f"{t}.{a}.o.b"] = f(P[f"{t}.{a}.to_out.0.bias"])
                     # GEGLU: 16 value rows then their 16 gate rows, so one accumulator chunk holds both halves
                     w1, b1 = P[t + ".ff.net.0.proj.weight"].detach(), P[t + ".ff.net.0.proj.bias"].detach()
-                    W[t + ".ff1.w"] = mat(geglu_pack(w1))
-                    W[t + ".ff1.b"] = geglu_pack(b1).to(F32).contiguous()
+                    if fold:
+                        wf, sf, tf = self._ln_fold_pack(w1, b1, W[t + ".norm3.g"], W[t + ".norm3.b"], pack=geglu_pack)
+                        W[t + ".ff1.w"], W[t + ".ff1.s"], W[t + ".ff1.b"] = wf, sf, tf
+                    else:
+                        W[t + ".ff1.w"] = mat(geglu_pack(w1))
+                        W[t + ".ff1.b"] = geglu_pack(b1).to(F32).contiguous()
                     W[t + ".ff2.w"] = mat(P[t + ".ff.net.2.weight"]); W[t + ".ff2.b"] = f(P[t + ".ff.net.2.bias"])
             elif st.kind == "down":
                 W[k + ".w"] = mat(_conv3_matrix(P[k + ".op.weight"]), 9); W[k + ".b"] = f(P[k + ".op.bias"])
@@ -130,6 +142,25 @@ class Engine:
         W["emb.w"] = small(torch.cat(emb_w, 0))
         W["emb.b"] = torch.cat(emb_b, 0).to(F32).contiguous()
         return W
+
+    def _fold_ln(self, c: int) -> bool:
+        ops = self.ops
+        return bool(getattr(ops, "fold_layernorm", False)) and c <= ops.LN_FOLD_MAX_C and (c % 160 == 0 or c % 128 == 0)
+
+    @staticmethod
+    def _ln_fold_pack(w, bias, gamma, beta, pack=None):
+        """nn.LayerNorm(C) followed by nn.Linear W (attention.py:699-701, 732-747) as ONE GEMM on the un-normalised rows:
+        LN(y) W^T = rstd (y W'^T - mean s) + t with W' = W diag(gamma), s_n = sum_k W'[n,k] (of the bf16-rounded W' the MMA
+        multiplies), t_n = sum_k beta_k W[n,k] (+ bias_n). Returns (bf16 W', fp32 s, fp32 t), optionally row-permuted."""
+        w = w.detach().to(F32)
+        wp = (w * gamma.to(w.device)[None, :]).to(torch.bfloat16)
+        s = wp.to(F32).sum(1)
+        t = w @ beta.to(w.device)
+        if bias is not None:
+            t = t + bias.detach().to(F32)
+        if pack is not None:
+            wp, s, t = pack(wp), pack(s), pack(t)
+        return wp.contiguous(), s.contiguous(), t.contiguous()
 
     def pack(self, unet_params: dict | None, cn_params: dict | None) -> None:
         """(Re)build packed weights from fp32 parameters keyed by the reference's state-dict names
@@ -249,6 +280,8 @@ class Engine:
         ops = self.ops
         dt = ops.qkv_dtype
         Fr, H, Wd, C, b, T = geom
+        if W[t + ".fold"]:
+            return self._transformer_folded(W, t, y, heads, mode, geom, kv)
         n1 = ops.layernorm(y, W[t + ".norm1.g"], W[t + ".norm1.b"])
         qkv = ops.gemm(n1, W[t + ".qkv.w"], out_dtype=dt)
         if mode == "temporal":
@@ -270,6 +303,28 @@ class Engine:
             return ops.gemm(ff, W[t + ".ff2.w"], bias=W[t + ".ff2.b"], residual=y, out_dtype=torch.bfloat16)
         return ops.gemm(ff, W[t + ".ff2.w"], bias=W[t + ".ff2.b"], residual=y, out=y, out_dtype=tok)
 
+    def _transformer_folded(self, W, t: str, ys, heads, mode, geom, kv):
+        """The same block with the three LayerNorms folded into the GEMMs around the bf16 token stream: every GEMM that
+        writes the stream also emits the per-row (sum, sum of squares) of what it stored, and the GEMM that consumes
+        LN(stream) multiplies the un-normalised stream by W diag(gamma) and finishes the normalisation in its epilogue.
+        No LayerNorm kernel, no normalised copy of the stream."""
+        ops, dt = self.ops, self.ops.qkv_dtype
+        Fr, H, Wd, C, b, T = geom
+        y, st = ys                                       # stream + row statistics from proj_in
+        eps = 1e-5
+        qkv = ops.gemm(y, W[t + ".qkv.w"], bias=W[t + ".qkv.t"], out_dtype=dt, ln=(st, W[t + ".qkv.s"], eps))
+        if mode == "temporal":
+            o = ops.attention_temporal(qkv.view(b, T, H * Wd, 3 * C), heads)
+        else:
+            V = self.cfg.num_views
+            o = ops.attention_view(qkv.view(Fr, H, V, Wd // V, 3 * C), heads, mode == "cross", CROSS_VIEW_NEIGHBOURS)
+        y, st = ops.gemm(o.view(-1, C), W[t + ".attn1.o.w"], bias=W[t + ".attn1.o.b"], residual=y, out=y, out_dtype=y.dtype, ln_stats_out=True)
+        q = ops.gemm(y, W[t + ".q2.w"], bias=W[t + ".q2.t"], out_dtype=dt, ln=(st, W[t + ".q2.s"], eps))
+        o = ops.attention_text(q.view(b, T * H * Wd, C), kv, heads)
+        y, st = ops.gemm(o.view(-1, C), W[t + ".attn2.o.w"], bias=W[t + ".attn2.o.b"], residual=y, out=y, out_dtype=y.dtype, ln_stats_out=True)
+        ff = ops.gemm(y, W[t + ".ff1.w"], bias=W[t + ".ff1.b"], geglu=True, out_dtype=ops.act_dtype, ln=(st, W[t + ".ff1.s"], eps))
+        return ops.gemm(ff, W[t + ".ff2.w"], bias=W[t + ".ff2.b"], residual=y, out_dtype=torch.bfloat16)
+
     def _stt(self, W, st: Stage, x):
         """SpatialTemporalTransformer.forward (attention.py:1064-1134): intra-view, cross-view, temporal."""
         ops, k, T = self.ops, st.key, self.cfg.num_frames
@@ -278,14 +333,15 @@ class Engine:
         geom = (Fr, H, Wd, C, b, T)
         for br, mode in zip(STT_BRANCHES, ("intra", "cross", "temporal")):
             a = ops.groupnorm(x, W[f"{k}.norm{br}.g"], W[f"{k}.norm{br}.b"], 1e-6, False)
+            t = f"{k}.transformer_blocks{br}.0"
+            fold = {"ln_stats_out": True} if W[t + ".fold"] else {}
             if mode == "temporal":
                 pe = self._pos_table(T, C, x.device)
                 y = ops.gemm(a.view(-1, a.shape[-1]), W[f"{k}.proj_in{br}.w"], bias=W[f"{k}.proj_in{br}.b"], rowvec=pe,
-                             rows_per_group=H * Wd, n_groups=T, out_dtype=ops.token_dtype)
+                             rows_per_group=H * Wd, n_groups=T, out_dtype=ops.token_dtype, **fold)
             else:
                 y = ops.gemm(a.view(-1, a.shape[-1]), W[f"{k}.proj_in{br}.w"], bias=W[f"{k}.proj_in{br}.b"],
-                             out_dtype=ops.token_dtype)
-            t = f"{k}.transformer_blocks{br}.0"
+                             out_dtype=ops.token_dtype, **fold)
             y = self._transformer(W, t, y, st.heads, mode, geom, self.cond["kv"][(W.tag, t)])
             yb = self._to_operand(y) if y.dtype == F32 else y
             x = ops.gemm(yb, W[f"{k}.proj_out{br}.w"], bias=W[f"{k}.proj_out{br}.b"], residual=x, out=x).view(Fr, H, Wd, C)

@@ -61,6 +61,8 @@ class NativeOps:
     act_dtype = BF16          # dtype of intermediates consumed by CUDA-core kernels (hint stem, GEGLU output, head input)
     fused_operand_emit = True # a GEMM epilogue may store the next GEMM's operand directly (out_dtype=bf16)
     token_dtype = BF16        # token stream inside a transformer block (proj_in .. proj_out): 3 residual adds per block
+    fold_layernorm = True     # LayerNorm folded into the GEMMs around the bf16 token stream (C <= LN_FOLD_MAX_C)
+    LN_FOLD_MAX_C = 640       # the producers' streaming bf16 epilogue (which emits the row sums) covers K <= 640
 
     def __init__(self):
         import os
@@ -69,6 +71,8 @@ class NativeOps:
         self._freqs = {}
         if os.environ.get("PN_TOKEN_F32") == "1" and self.operand_mode == OP_BF16:      # A/B measurement of the bf16 token stream
             self.token_dtype = F32
+        if os.environ.get("PN_LN_FOLD") == "0" or self.token_dtype != BF16:              # A/B measurement of the LayerNorm fold
+            self.fold_layernorm = False
 
     def pack_matrix(self, w: torch.Tensor, taps: int = 1) -> torch.Tensor:
         """fp32 weight [N, taps*C] -> the B operand pn_gemm reads in this op set's precision mode."""
@@ -88,12 +92,15 @@ class NativeOps:
 
     # ------------------------------------------------------------------ GEMM / implicit conv
     def gemm(self, a, w, *, bias=None, rowvec=None, rows_per_group=0, n_groups=0, residual=None, residual2=None,
-             geglu=False, out_dtype=F32, taps=(1, 1), out=None):
+             geglu=False, out_dtype=F32, taps=(1, 1), out=None, ln=None, ln_stats_out=False):
         """out[row, :] = epi(sum_taps A[shifted pixel] @ w^T). See include/panacea_b200.h::pn_gemm.
 
         a: bf16 [..., C] (taps == (1,1): any leading dims, rows may be strided views with C contiguous)
            or bf16 [NB, H, W, C] for taps (3,3) / (3,1).
         w: bf16 [N, taps_h*taps_w*C].
+        ln = (stats fp32 [rows, parts, 2], colsum fp32 [N], eps): LayerNorm of the rows of `a` (the un-normalised bf16
+             token stream) folded into this GEMM, w = W diag(gamma), bias = W beta (+ bias); see pn_gemm_args.
+        ln_stats_out: also return the per-row partial (sum, sumsq) of the bf16 output rows: (out, stats).
         """
         _req(a.is_cuda and a.dtype == BF16 and w.dtype == BF16, "gemm: a and w must be CUDA bf16")
         _req(a.stride(-1) == 1 and w.is_contiguous(), "gemm: innermost dim must be contiguous")
@@ -160,9 +167,22 @@ class NativeOps:
         args.rows_per_group = rows_per_group; args.n_groups = n_groups
         args.out_bf16 = 1 if out_dtype == BF16 else 0
         args.geglu = 1 if geglu else 0
+        stats = None
+        if ln is not None:
+            st_in, colsum, eps = ln
+            _req(st_in.dtype == F32 and st_in.is_contiguous() and st_in.dim() == 3 and st_in.shape[0] == rows and st_in.shape[2] == 2,
+                 "gemm: ln stats must be fp32 [rows, parts, 2]")
+            _req(colsum.dtype == F32 and colsum.numel() == N, "gemm: ln colsum must be fp32 [N]")
+            args.ln_stats_in, args.ln_colsum, args.ln_parts_in, args.ln_eps = st_in.data_ptr(), colsum.data_ptr(), st_in.shape[1], float(eps)
+        if ln_stats_out:
+            parts = self.lib.pn_gemm_ln_parts(N)
+            _req(parts > 0, "gemm: ln_stats_out needs N % 160 == 0 or N % 128 == 0")
+            stats = torch.empty((rows, parts, 2), device=a.device, dtype=F32)
+            args.ln_stats_out = stats.data_ptr()
         _lib.check(self.lib.pn_gemm(C.byref(args), _stream()), "pn_gemm")
         self.launches += 1
-        return out.reshape(*lead, n_out) if out.is_contiguous() else out
+        res = out.reshape(*lead, n_out) if out.is_contiguous() else out
+        return (res, stats) if ln_stats_out else res
 
     # ------------------------------------------------------------------ normalisation
     def groupnorm(self, x, gamma, beta, eps, silu, want_raw=False, out_f32=False):
@@ -412,6 +432,7 @@ class ParityOps(NativeOps):
     act_dtype = F32
     fused_operand_emit = False
     token_dtype = F32
+    fold_layernorm = False
 
     def pack_matrix(self, w, taps=1):
         return split3(w, taps)

@@ -81,6 +81,39 @@ def test_gemm_bf16_token_stream_residual(ops, M, N, K):
     _check(out2, a.float() @ w.float().t() + y2.float(), tol=1e-2, name="bf16 residual")
 
 
+@pytest.mark.parametrize("M,C", [(3000, 320), (2500, 640), (172032 // 8, 320), (700, 128), (130, 512)])
+def test_gemm_layernorm_fold(ops, M, C):
+    """LayerNorm folded into the GEMMs around the bf16 token stream: (i) a producer (bf16 out + bf16 residual, streaming
+    epilogue) emits per-row partial sums of what it stores; (ii) consumers (plain bf16 streaming epilogue, and GEGLU) take
+    the un-normalised stream, W diag(gamma), the column sums and W beta, and must equal Linear(LayerNorm(stream))."""
+    from panacea_b200.engine import Engine
+    a = _rand((M, C), 30); wo = _rand((C, C), 31, C ** -0.5)
+    y0 = _rand((M, C), 32, 2.0) + 0.7
+    y, st = ops.gemm(a, wo, residual=y0.clone(), out_dtype=torch.bfloat16, ln_stats_out=True)
+    torch.cuda.synchronize()
+    assert st.shape == (M, 2 * (C // (160 if C % 160 == 0 else 128)), 2)
+    yf = y.float()
+    torch.testing.assert_close(st[..., 0].sum(1), yf.sum(1), rtol=1e-4, atol=1e-2)
+    torch.testing.assert_close(st[..., 1].sum(1), (yf * yf).sum(1), rtol=1e-4, atol=1e-2)
+    gamma = _rand((C,), 33, 0.2, dtype=torch.float32) + 1.0
+    beta = _rand((C,), 34, 0.2, dtype=torch.float32)
+    ln = F.layer_norm(yf, (C,), gamma, beta, 1e-5)
+    # consumer 1: q|k|v projection, no bias
+    wq = _rand((3 * C, C), 35, C ** -0.5, dtype=torch.float32)
+    wp, s, t = Engine._ln_fold_pack(wq, None, gamma, beta)
+    out = ops.gemm(y, wp, bias=t, out_dtype=torch.bfloat16, ln=(st, s, 1e-5))
+    torch.cuda.synchronize()
+    _check(out, ln @ wq.t(), tol=1.5e-2, name="LN fold -> linear")
+    # consumer 2: GEGLU feed-forward input projection with bias
+    w1 = _rand((8 * C, C), 36, C ** -0.5, dtype=torch.float32)
+    b1 = _rand((8 * C,), 37, dtype=torch.float32)
+    wp, s, t = Engine._ln_fold_pack(w1, b1, gamma, beta, pack=geglu_pack)
+    ff = ops.gemm(y, wp, bias=t, geglu=True, out_dtype=torch.bfloat16, ln=(st, s, 1e-5))
+    torch.cuda.synchronize()
+    h = ln @ w1.t() + b1
+    _check(ff, h[:, :4 * C] * F.gelu(h[:, 4 * C:]), tol=1.5e-2, name="LN fold -> GEGLU")
+
+
 def test_gemm_geglu(ops):
     M, C = 1500, 320
     a = _rand((M, C), 10)

@@ -9,7 +9,7 @@ from oracle import cases as Cs
 from oracle import unet_port as P
 from panacea_b200 import engine as E
 from panacea_b200 import netplan as NP
-from torch_ref_ops import TorchRefOps, TorchSplitOps
+from torch_ref_ops import TorchFoldOps, TorchRefOps, TorchSplitOps
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
 
@@ -75,6 +75,24 @@ def test_parity_mode_split_operands_reach_fp32_class_accuracy(name):
     frac = (d <= 1e-4 + 1e-3 * g.abs()).float().mean().item()
     rel = ((eps - g).norm() / g.norm()).item()
     assert frac >= 0.999 and rel < 1e-4, (frac, rel)
+
+
+def test_layernorm_fold_orchestration_matches_reference_golden():
+    """Fast-path orchestration with the three LayerNorms of every transformer block folded into the GEMMs around the
+    token stream (row sums from the producer epilogue, W diag(gamma) + rank-1 correction in the consumer): must reproduce
+    the reference golden up to the bf16 rounding of the folded weights."""
+    case = [c for c in Cs.GOLDEN_CASES if c.name == "small_hd64"][0]
+    cfg = NP.config_from_kwargs(case.unet_kwargs())
+    ops = TorchFoldOps()
+    eng = E.Engine(cfg, ops)
+    eng.pack(*_split(Cs.make_weights(case)))
+    assert any(v is True for k, v in eng.wu.items() if k.endswith(".fold"))
+    x, t, c = Cs.make_inputs(case)
+    eng.prepare_condition(c["cond_feat"], c["crossattn"])
+    eps = eng.eps(x, c["concat"], t)
+    g = torch.load(GOLDEN / "eps_small_hd64.pt")["eps"]
+    rel = ((eps - g).norm() / g.norm()).item()
+    assert rel < 3e-3, rel                                  # bf16-rounded W diag(gamma); a wrong fold is O(1) off
 
 
 def test_dropin_modules_share_the_reference_state_dict():

@@ -22,6 +22,7 @@ class TorchRefOps:
     act_dtype = F32
     fused_operand_emit = False
     token_dtype = F32
+    fold_layernorm = False
 
     def __init__(self):
         self.launches = 0
@@ -33,7 +34,7 @@ class TorchRefOps:
         return w.detach().to(F32).contiguous()
 
     def gemm(self, a, w, *, bias=None, rowvec=None, rows_per_group=0, n_groups=0, residual=None, residual2=None,
-             geglu=False, out_dtype=F32, taps=(1, 1), out=None):
+             geglu=False, out_dtype=F32, taps=(1, 1), out=None, ln=None, ln_stats_out=False):
         th, tw = taps
         C = a.shape[-1]
         N = w.shape[0]
@@ -41,6 +42,12 @@ class TorchRefOps:
         if (th, tw) == (1, 1):
             lead = a.shape[:-1]
             y = a.float().reshape(-1, C) @ wf.t()
+            if ln is not None:      # pn_gemm_args.ln_*: finish the folded LayerNorm from the producer's partial row sums
+                st, colsum, eps = ln
+                sm, sq = st[..., 0].sum(1), st[..., 1].sum(1)
+                mu = sm / C
+                rstd = torch.rsqrt((sq / C - mu * mu).clamp_min(0) + eps)
+                y = rstd[:, None] * (y - mu[:, None] * colsum[None, :])
         else:
             NB, H, W, _ = a.shape
             lead = (NB, H, W)
@@ -64,10 +71,23 @@ class TorchRefOps:
         if residual2 is not None:
             y = y + residual2.reshape(rows, -1)
         y = y.to(out_dtype)
+        stats = None
+        if ln_stats_out:            # two partial (sum, sumsq) pairs per 160-wide column tile, like the streaming epilogue
+            yy = y.float()
+            n = yy.shape[1]
+            bn = 160 if n % 160 == 0 else 128
+            parts = []
+            for c0 in range(0, n, bn):
+                for chunks in ((0, 2, 4), (1, 3)) if bn == 160 else ((0, 2), (1, 3)):
+                    cols = torch.cat([yy[:, c0 + 32 * c:c0 + 32 * c + 32] for c in chunks], 1)
+                    parts.append(torch.stack([cols.sum(1), (cols * cols).sum(1)], -1))
+            stats = torch.stack(parts, 1).contiguous()
         if out is not None:
             out.reshape(rows, -1).copy_(y)
-            return out.reshape(*lead, y.shape[1])
-        return y.reshape(*lead, y.shape[1])
+            res = out.reshape(*lead, y.shape[1])
+        else:
+            res = y.reshape(*lead, y.shape[1])
+        return (res, stats) if ln_stats_out else res
 
     def groupnorm(self, x, gamma, beta, eps, silu, want_raw=False, out_f32=False):
         Fr, C = x.shape[0], x.shape[-1]
@@ -189,6 +209,13 @@ class TorchRefOps:
 
     def scale_dup(self, x, s, copies):
         return torch.cat([x * s] * copies)
+
+
+class TorchFoldOps(TorchRefOps):
+    """TorchRefOps with the LayerNorm fold switched on (the NativeOps fast-path orchestration: row statistics from the
+    producers of the token stream, W diag(gamma) / column sums / W beta in the consumers), fp32 stream on CPU."""
+    fold_layernorm = True
+    LN_FOLD_MAX_C = 640
 
 
 def _enc(x):
