@@ -536,7 +536,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
         ln_mu = sm * p.ln_inv_dim;
         ln_rstd = rsqrtf(fmaxf(sq * p.ln_inv_dim - ln_mu * ln_mu, 0.f) + p.ln_eps);
       }
-      float st_sum = 0.f, st_sq = 0.f;                            // partial row sums of what this thread stores (producer)
+      f32x2 st_sum2 = 0ull, st_sq2 = 0ull;                        // partial row sums of what this thread stores (producer)
       { const long long w0 = dbg ? clock64() : 0; mbar_wait(&tmem_full[acc], acc_phase); if (dbg) d_tf += clock64() - w0; }
       tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t(lane_grp * 32) << 16) + acc * BN;
@@ -560,14 +560,16 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
           if (MODE == 5 && p.ln_stats_in != nullptr) {
+            // out = rstd * acc + (-rstd * mean) * s_n + t_n : two packed FMAs per pair, bias (= t_n) included
+            const f32x2 a2 = f2_splat(ln_rstd), b2 = f2_splat(-ln_rstd * ln_mu);
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + n0 + j));
-              f[j] = ln_rstd * fmaf(-ln_mu, s4.x, f[j]); f[j + 1] = ln_rstd * fmaf(-ln_mu, s4.y, f[j + 1]);
-              f[j + 2] = ln_rstd * fmaf(-ln_mu, s4.z, f[j + 2]); f[j + 3] = ln_rstd * fmaf(-ln_mu, s4.w, f[j + 3]);
+              const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+              f2_unpack(f2_fma(a2, f2_pack(f[j], f[j + 1]), f2_fma(b2, f2_pack(s4.x, s4.y), f2_pack(t4.x, t4.y))), f[j], f[j + 1]);
+              f2_unpack(f2_fma(a2, f2_pack(f[j + 2], f[j + 3]), f2_fma(b2, f2_pack(s4.z, s4.w), f2_pack(t4.z, t4.w))), f[j + 2], f[j + 3]);
             }
-          }
-          if (p.bias != nullptr) {
+          } else if (p.bias != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
@@ -602,13 +604,12 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
               const uint4 o4 = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
                                           pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
               *q = o4;
-              if (p.ln_stats_out != nullptr) {           // sums of the ROUNDED values: what the consumer's MMA will read
-                const uint32_t w4[4] = {o4.x, o4.y, o4.z, o4.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float lo = __uint_as_float(w4[e] << 16), hi = __uint_as_float(w4[e] & 0xffff0000u);
-                  st_sum += lo + hi;
-                  st_sq = fmaf(lo, lo, fmaf(hi, hi, st_sq));
+              if (p.ln_stats_out != nullptr) {           // row sums of the fp32 values (their bf16 rounding, which the
+#pragma unroll                                           // consumer's MMA reads, perturbs mean / variance by < 2^-9 / sqrt(C))
+                for (int e = 0; e < 8; e += 2) {
+                  const f32x2 pr = f2_pack(f[8 * j + e], f[8 * j + e + 1]);
+                  st_sum2 = f2_add(st_sum2, pr);
+                  st_sq2 = f2_fma(pr, pr, st_sq2);
                 }
               }
             }
@@ -630,8 +631,12 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
           if (lane == 0) mbar_arrive(&c_ready[c]);
         }
       }
-      if (MODE == 5 && p.ln_stats_out != nullptr && row_ok)
-        reinterpret_cast<float2*>(p.ln_stats_out)[grow * p.ln_parts_out + tcol * 2 + half] = make_float2(st_sum, st_sq);
+      if (MODE == 5 && p.ln_stats_out != nullptr && row_ok) {
+        float s0, s1, q0, q1;
+        f2_unpack(st_sum2, s0, s1);
+        f2_unpack(st_sq2, q0, q1);
+        reinterpret_cast<float2*>(p.ln_stats_out)[grow * p.ln_parts_out + tcol * 2 + half] = make_float2(s0 + s1, q0 + q1);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (dbg && lane == 0) {
@@ -747,15 +752,15 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
           if (MODE == 2 && p.ln_stats_in != nullptr) {
-            const f32x2 nmu = f2_splat(-ln_mu), rs = f2_splat(ln_rstd);
+            const f32x2 a2 = f2_splat(ln_rstd), b2 = f2_splat(-ln_rstd * ln_mu);
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 s4 = *reinterpret_cast<const float4*>(my_colsum + k * 32 + j);
-              f2_unpack(f2_mul(rs, f2_fma(nmu, f2_pack(s4.x, s4.y), f2_pack(f[j], f[j + 1]))), f[j], f[j + 1]);
-              f2_unpack(f2_mul(rs, f2_fma(nmu, f2_pack(s4.z, s4.w), f2_pack(f[j + 2], f[j + 3]))), f[j + 2], f[j + 3]);
+              const float4 t4 = *reinterpret_cast<const float4*>(my_bias + k * 32 + j);
+              f2_unpack(f2_fma(a2, f2_pack(f[j], f[j + 1]), f2_fma(b2, f2_pack(s4.x, s4.y), f2_pack(t4.x, t4.y))), f[j], f[j + 1]);
+              f2_unpack(f2_fma(a2, f2_pack(f[j + 2], f[j + 3]), f2_fma(b2, f2_pack(s4.z, s4.w), f2_pack(t4.z, t4.w))), f[j + 2], f[j + 3]);
             }
-          }
-          if (p.bias != nullptr) {
+          } else if (p.bias != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1025,6 +1030,7 @@ extern "C" int pn_gemm(const pn_gemm_args* a, void* stream_v) {
                                    "pn_gemm: a bf16 residual needs bf16 output, no GEGLU, no second residual, ldr%%8==0");
   if (a->residual2) PN_REQUIRE(!a->out_bf16 && !a->geglu && a->ldr2 >= a->N && a->ldr2 % 4 == 0, "pn_gemm: residual2 needs fp32 out and a valid ldr2");
   if (a->rowvec) PN_REQUIRE(a->rows_per_group > 0 && a->n_groups > 0, "pn_gemm: rowvec needs rows_per_group/n_groups");
+  if (a->ln_stats_in) PN_REQUIRE(a->bias != nullptr, "pn_gemm: a folded LayerNorm needs bias = W beta (+ bias)");
   if (a->ln_stats_in) PN_REQUIRE(a->ln_colsum && a->ln_parts_in > 0 && a->ln_parts_in <= 64 && a->out_bf16 && a->taps_h == 1 && a->taps_w == 1,
                                  "pn_gemm: a folded LayerNorm needs ln_colsum, 1..64 partial sums per row, a 1x1 GEMM and bf16 output");
 
