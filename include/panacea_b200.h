@@ -162,9 +162,10 @@ int pn_layernorm(const void* x, int x_is_bf16, const float* gamma, const float* 
 int pn_conv3x3_direct(const void* x, int x_is_bf16, const float* w_packed, const float* bias, const float* addend,
                       float* y_f32, void* y_bf16, int64_t frames, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
                       int64_t Cout_pad, int stride, int act_silu, void* stream);
-/* im2col for the stride-2 Downsample conv (openaimodel.py:187): fp32 [F,H,W,C] -> operand [F*Ho*Wo, 9 taps x C]
- * (each tap is one operand row of C channels: 9*C bf16, or 9*3C in split3 mode). */
-int pn_im2col3x3_s2(const float* x, void* out, int64_t frames, int64_t H, int64_t W, int64_t C, int operand_mode,
+/* im2col for the stride-2 Downsample conv: fp32 [F,H,W,C] -> operand [F*Ho*Wo, 9 taps x C] (each tap is one operand
+ * row of C channels: 9*C bf16, or 9*3C in split3 mode). pad = 1: Conv2d(3, stride 2, padding 1) of the UNet
+ * (openaimodel.py:187); pad = 0: the VAE encoder's F.pad(x, (0,1,0,1)) + Conv2d(3, stride 2, padding 0) (model.py:98-113). */
+int pn_im2col3x3_s2(const float* x, void* out, int64_t frames, int64_t H, int64_t W, int64_t C, int pad, int operand_mode,
                     void* stream);
 /* F.interpolate(scale_factor=2, mode="nearest") of Upsample (openaimodel.py:133-140), fp32 -> operand. */
 int pn_upsample2x(const float* x, void* y, int64_t frames, int64_t H, int64_t W, int64_t C, int operand_mode, void* stream);

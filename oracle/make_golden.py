@@ -139,7 +139,24 @@ def golden_vae_decode() -> dict:
     pq.load_state_dict({"weight": sd["post_quant_conv.weight"], "bias": sd["post_quant_conv.bias"]})
     z = vae_decoder_input()
     out = dec(pq(z))
-    return {"ddconfig": VAE_DDCONFIG, "image": out.contiguous(), "keys": sorted(spec)}
+    # encoder: moments = quant_conv(Encoder(x)) (autoencoder.py:352-357)
+    from panacea_b200.vae import encoder_param_spec
+    espec = encoder_param_spec(VAE_DDCONFIG, 4)
+    esd = vae_decoder_weights(espec, seed=9)
+    with contextlib.redirect_stdout(io.StringIO()):
+        enc = M.Encoder(**VAE_DDCONFIG).eval()
+    enc.load_state_dict({k[len("encoder."):]: v for k, v in esd.items() if k.startswith("encoder.")}, strict=True)
+    qc = torch.nn.Conv2d(8, 8, 1)
+    qc.load_state_dict({"weight": esd["quant_conv.weight"], "bias": esd["quant_conv.bias"]})
+    x = vae_encoder_input()
+    moments = qc(enc(x))
+    return {"ddconfig": VAE_DDCONFIG, "image": out.contiguous(), "keys": sorted(spec), "moments": moments.contiguous(),
+            "encoder_keys": sorted(espec)}
+
+
+def vae_encoder_input(seed: int = 10):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return torch.rand(2, 3, 32, 192, generator=g) * 2.0 - 1.0       # 2 frames, 32 x (6 views x 32) pixels
 
 
 def sampler_inputs(case: Cs.EpsCase, use_last_frame: bool = False):

@@ -64,7 +64,7 @@ SIGNATURES: dict[str, tuple] = {
     "pn_layernorm": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _i64, _i64, _f32, C.c_int, _vp]),
     "pn_conv3x3_direct": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64,
                                     C.c_int, C.c_int, _vp]),
-    "pn_im2col3x3_s2": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, C.c_int, _vp]),
+    "pn_im2col3x3_s2": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, C.c_int, C.c_int, _vp]),
     "pn_upsample2x": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, C.c_int, _vp]),
     "pn_concat_add": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "pn_add_inplace": (C.c_int, [_vp, _vp, _i64, _vp]),

@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(128) linear_small_kernel(const float* __restri
 // (viewed by the GEMM as [rows, 9*C] or [rows, 9*3C]: every tap is one operand row)
 template <int OP>
 __global__ void im2col_s2_kernel(const float* __restrict__ x, void* __restrict__ out, int F, int H, int W, int C,
-                                 int Ho, int Wo) {
+                                 int Ho, int Wo, int pad) {
   pdl_prologue_done();
   const int c8n = C / 8;
   const size_t total = (size_t)F * Ho * Wo * 9 * c8n;
@@ -210,7 +210,7 @@ __global__ void im2col_s2_kernel(const float* __restrict__ x, void* __restrict__
     const int ox = (int)(r % Wo); r /= Wo;
     const int oy = (int)(r % Ho);
     const int f = (int)(r / Ho);
-    const int iy = oy * 2 - 1 + tap / 3, ix = ox * 2 - 1 + tap % 3;
+    const int iy = oy * 2 - pad + tap / 3, ix = ox * 2 - pad + tap % 3;
     float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
       const float* src = x + (((size_t)f * H + iy) * W + ix) * C + c8 * 8;
@@ -431,14 +431,16 @@ extern "C" int pn_linear_small(const float* x, const void* W_any, int w_is_f32, 
   return PN_OK;
 }
 
-extern "C" int pn_im2col3x3_s2(const float* x, void* out, int64_t frames, int64_t H, int64_t W, int64_t C, int operand_mode,
-                               void* stream_v) {
+extern "C" int pn_im2col3x3_s2(const float* x, void* out, int64_t frames, int64_t H, int64_t W, int64_t C, int pad,
+                               int operand_mode, void* stream_v) {
   PN_REQUIRE(x && out && frames > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "pn_im2col3x3_s2: bad arguments");
   PN_REQUIRE(operand_mode == PN_OP_BF16 || operand_mode == PN_OP_SPLIT3, "pn_im2col3x3_s2: operand_mode %d", operand_mode);
-  const int Ho = (int)((H + 2 - 3) / 2 + 1), Wo = (int)((W + 2 - 3) / 2 + 1);
+  PN_REQUIRE(pad == 0 || pad == 1, "pn_im2col3x3_s2: pad must be 1 (symmetric) or 0 (zero row/column appended at the far edges)");
+  // pad 1: Conv2d(k3, s2, padding=1); pad 0: F.pad(x, (0,1,0,1)) + Conv2d(k3, s2, padding=0) (the VAE encoder's Downsample)
+  const int Ho = (int)((H + 2 * pad + (1 - pad) - 3) / 2 + 1), Wo = (int)((W + 2 * pad + (1 - pad) - 3) / 2 + 1);
   const size_t total = (size_t)frames * Ho * Wo * 9 * (C / 8);
   PN_DISPATCH_OP(operand_mode, (launch_kernel(im2col_s2_kernel<OP>, dim3(grid_for(total)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream_v), 1, 
-      x, out, (int)frames, (int)H, (int)W, (int)C, Ho, Wo)));
+      x, out, (int)frames, (int)H, (int)W, (int)C, Ho, Wo, pad)));
   PN_CHECK_CUDA(cudaGetLastError());
   return PN_OK;
 }

@@ -4,8 +4,9 @@ model built from `configs/inference_nuscenes.yaml`-style YAML via instantiate_fr
 writers. SURVEY.md section 8f rows N1 (engine / conditioner glue) and N3 (writers, gather -> rank-0 writer).
 
 What is NOT here, and why: the nuScenes dataset + BEV rasteriser (row N4, needs nuScenes and mmdet3d) is replaced by
-`SyntheticBEVDataset` with the same batch contract; the CLIP / VAE towers are deterministic stand-ins (BASELINE.json
-configs[3]). With the real modules importable, `--dataset module:Class` and the YAML targets swap them in.
+`SyntheticBEVDataset` with the same batch contract; the CLIP text tower is a deterministic stand-in (BASELINE.json
+configs[3]); the VAE (encoder and decoder) is native and random-init unless a checkpoint provides `first_stage_model.*`.
+With the real modules importable, `--dataset module:Class` and the YAML targets swap them in.
 
   torchrun --nproc-per-node 8 -m panacea_b200.inference --base configs.yaml --name run1 --inferdir out --gather
 """

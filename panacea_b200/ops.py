@@ -301,12 +301,12 @@ class NativeOps:
         self.launches += 1
         return y
 
-    def im2col_s2(self, x):
+    def im2col_s2(self, x, pad=1):
         _req(x.is_cuda and x.dtype == F32 and x.is_contiguous() and x.dim() == 4, "im2col_s2: x fp32 [F,H,W,C]")
         Fr, H, W, Cc = x.shape
-        Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        Ho, Wo = ((H - 1) // 2 + 1, (W - 1) // 2 + 1) if pad == 1 else ((H - 2) // 2 + 1, (W - 2) // 2 + 1)
         out = torch.empty((Fr * Ho * Wo, 9 * self.operand_mult * Cc), device=x.device, dtype=BF16)
-        _lib.check(self.lib.pn_im2col3x3_s2(_ptr(x), _ptr(out), Fr, H, W, Cc, self.operand_mode, _stream()), "pn_im2col3x3_s2")
+        _lib.check(self.lib.pn_im2col3x3_s2(_ptr(x), _ptr(out), Fr, H, W, Cc, pad, self.operand_mode, _stream()), "pn_im2col3x3_s2")
         self.launches += 1
         return out, (Fr, Ho, Wo)
 

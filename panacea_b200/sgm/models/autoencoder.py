@@ -3,9 +3,10 @@
 * `decode(z)` — the KL autoencoder's DECODER runs natively on the hot path's kernels
   (`panacea_b200.vae.VAEDecoderEngine`); parameters live under the reference's state-dict names (`decoder.*`,
   `post_quant_conv.*`), so an SD-2.1 VAE checkpoint loads unchanged (`load_state_dict(strict=False)`).
-* `encode(x)` — the ENCODER is used once per sample on the image-condition frame; it is not built here. It is a
-  deterministic random-init 8x8 patch projection with the right tensor contract (BASELINE.json configs[3]: "random-init
-  VAE/CLIP stubs"), NOT a trained encoder; `encoder.*` / `quant_conv.*` checkpoint keys are ignored."""
+* `encode(x)` — the ENCODER (`quant_conv(Encoder(x))`, model.py:763-880) runs natively too
+  (`panacea_b200.vae.VAEEncoderEngine`, `encoder.*` / `quant_conv.*` keys); the posterior is sampled like the reference
+  (distributions.py:24-41: mean + exp(0.5 clamp(logvar, -30, 20)) * randn drawn on the CPU generator).
+Without a checkpoint the parameters are random-init (BASELINE.json configs[3]: "random-init VAE/CLIP stubs")."""
 from __future__ import annotations
 
 import math
@@ -13,7 +14,7 @@ import math
 import torch
 import torch.nn as nn
 
-from ...vae import VAEDecoderEngine, decoder_param_spec
+from ...vae import VAEDecoderEngine, VAEEncoderEngine, decoder_param_spec, encoder_param_spec
 
 
 class AutoencoderKLInferenceWrapper(nn.Module):
@@ -25,7 +26,7 @@ class AutoencoderKLInferenceWrapper(nn.Module):
         self.ddconfig, self.embed_dim = dd, embed_dim
         self.factor = 2 ** (len(dd["ch_mult"]) - 1)
         g = torch.Generator().manual_seed(seed)
-        self._spec = decoder_param_spec(dd, embed_dim)
+        self._spec = {**decoder_param_spec(dd, embed_dim), **encoder_param_spec(dd, embed_dim)}
         self._attr = {k: "p__" + k.replace(".", "__") for k in self._spec}
         for k, shape in self._spec.items():
             p = torch.empty(shape)
@@ -36,14 +37,10 @@ class AutoencoderKLInferenceWrapper(nn.Module):
             else:
                 p.copy_(torch.randn(shape, generator=g) * (1.0 / math.sqrt(math.prod(shape[1:]))))
             self.register_parameter(self._attr[k], nn.Parameter(p, requires_grad=False))
-        # encoder stand-in (see the module docstring)
-        f, ci, cz = self.factor, dd["in_channels"], dd["z_channels"]
-        self.stub_encoder = nn.Conv2d(ci, cz, f, stride=f)
-        with torch.no_grad():
-            for p in self.stub_encoder.parameters():
-                p.copy_(torch.randn(p.shape, generator=g) * (1.0 / max(p[0].numel(), 1)) ** 0.5)
         self._engine = None
-        self._version, self._packed = 0, -1
+        self._enc_engine = None
+        self._version, self._packed, self._enc_packed = 0, -1, -1
+        self.sample_posterior = True
 
     # --- reference key names
     def _save_to_state_dict(self, destination, prefix, keep_vars):
@@ -73,9 +70,25 @@ class AutoencoderKLInferenceWrapper(nn.Module):
         return {k: getattr(self, a) for k, a in self._attr.items()}
 
     @torch.no_grad()
+    def encode_moments(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("panacea_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+        if self._enc_engine is None:
+            from ...ops import NativeOps
+            self._enc_engine = VAEEncoderEngine(self.ddconfig, NativeOps(), self.embed_dim)
+        if self._enc_packed != self._version:
+            self._enc_engine.pack(self.decoder_parameters())
+            self._enc_packed = self._version
+        return self._enc_engine.encode_moments(x)
+
+    @torch.no_grad()
     def encode(self, x):
-        """Stand-in for autoencoder.py:366-368 (posterior sample of the KL encoder): deterministic patch projection."""
-        return self.stub_encoder(x.float())
+        """autoencoder.py:352-357 + :366-368: a sample of the posterior N(mean, exp(logvar)) (distributions.py:24-41)."""
+        mean, logvar = torch.chunk(self.encode_moments(x), 2, dim=1)
+        if not self.sample_posterior:
+            return mean.contiguous()
+        std = torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0))
+        return mean + std * torch.randn(mean.shape).to(mean.device)      # CPU generator draw, like the reference
 
     @torch.no_grad()
     def decode(self, z):

@@ -1,4 +1,5 @@
-"""VAE decoder on the hot path's own kernels: the step right after the denoising loop.
+"""VAE decoder and encoder on the hot path's own kernels: the steps right after / before
+the denoising loop.
 
 Executes the reference's `AutoencoderKL.decode` = `Decoder(post_quant_conv(z))`
 (sgm/models/autoencoder.py:362-365; sgm/modules/diffusionmodules/model.py:882-1030: conv_in, mid = ResnetBlock /
@@ -58,7 +59,74 @@ def decoder_param_spec(dd: dict, embed_dim: int = 4) -> dict:
     return spec
 
 
-class VAEDecoderEngine:
+def encoder_param_spec(dd: dict, embed_dim: int = 4) -> dict:
+    """Keys/shapes of `encoder.*` + `quant_conv` (model.py:763-853; autoencoder.py:352-353)."""
+    ch, ch_mult, nrb, zc, cin = dd["ch"], tuple(dd["ch_mult"]), dd["num_res_blocks"], dd["z_channels"], dd["in_channels"]
+    if dd.get("attn_resolutions") or not dd.get("double_z", True):
+        raise NotImplementedError("attn_resolutions must be empty and double_z true (the SD-2.1 VAE of the reference config)")
+    spec = {"quant_conv.weight": (2 * embed_dim, 2 * zc, 1, 1), "quant_conv.bias": (2 * embed_dim,)}
+
+    def conv(k, co, ci, ks):
+        spec[k + ".weight"] = (co, ci, ks, ks)
+        spec[k + ".bias"] = (co,)
+
+    def norm(k, c):
+        spec[k + ".weight"] = (c,)
+        spec[k + ".bias"] = (c,)
+
+    def res(k, ci, co):
+        norm(k + ".norm1", ci); conv(k + ".conv1", co, ci, 3); norm(k + ".norm2", co); conv(k + ".conv2", co, co, 3)
+        if ci != co:
+            conv(k + ".nin_shortcut", co, ci, 1)
+
+    conv("encoder.conv_in", ch, cin, 3)
+    in_mult = (1,) + ch_mult
+    block_in = ch
+    for lvl in range(len(ch_mult)):
+        block_in, block_out = ch * in_mult[lvl], ch * ch_mult[lvl]
+        for i in range(nrb):
+            res(f"encoder.down.{lvl}.block.{i}", block_in, block_out)
+            block_in = block_out
+        if lvl != len(ch_mult) - 1:
+            conv(f"encoder.down.{lvl}.downsample.conv", block_in, block_in, 3)
+    res("encoder.mid.block_1", block_in, block_in)
+    norm("encoder.mid.attn_1.norm", block_in)
+    for n in ("q", "k", "v", "proj_out"):
+        conv(f"encoder.mid.attn_1.{n}", block_in, block_in, 1)
+    res("encoder.mid.block_2", block_in, block_in)
+    norm("encoder.norm_out", block_in)
+    conv("encoder.conv_out", 2 * zc, block_in, 3)
+    return spec
+
+
+class _VAEBlocks:
+    """ResnetBlock / AttnBlock / packing shared by the decoder and encoder engines."""
+
+    def _pack_common(self, P: dict, direct: tuple) -> dict:
+        f = lambda t: t.detach().to(F32).contiguous()
+        mat = self.ops.pack_matrix
+        W = {}
+        for k in self.spec:
+            if k.endswith(".weight") and ".norm" in k:
+                W[k[:-7] + ".g"], W[k[:-7] + ".b"] = f(P[k]), f(P[k[:-6] + "bias"])
+        for k, shape in self.spec.items():
+            if not k.endswith(".weight") or len(shape) != 4 or k in direct:
+                continue
+            base = k[:-7]
+            W[base + ".w"] = mat(_conv3_matrix(P[k]), 9) if shape[2] == 3 else mat(P[k].detach().reshape(shape[0], shape[1]))
+            W[base + ".b"] = f(P[base + ".bias"])
+        return W
+
+    @staticmethod
+    def _pack_1x1_direct(w):
+        """a 1x1 conv on few channels as the centre tap of the CUDA-core direct 3x3 conv"""
+        w = w.detach().to(F32)
+        w3 = torch.zeros(w.shape[0], w.shape[1], 3, 3, device=w.device)
+        w3[:, :, 1, 1] = w[:, :, 0, 0]
+        return _pack_direct(w3)
+
+
+class VAEDecoderEngine(_VAEBlocks):
     def __init__(self, ddconfig: dict, ops, embed_dim: int = 4):
         self.dd, self.ops, self.embed_dim = dict(ddconfig), ops, embed_dim
         self.spec = decoder_param_spec(self.dd, embed_dim)
@@ -67,27 +135,10 @@ class VAEDecoderEngine:
     # ------------------------------------------------------------------------------------------ packing
     def pack(self, P: dict) -> None:
         f = lambda t: t.detach().to(F32).contiguous()
-        mat = self.ops.pack_matrix
-        W = {}
-        # post_quant_conv (1x1, 4 -> 4) as the centre tap of a direct 3x3 conv
-        w = P["post_quant_conv.weight"].detach().to(F32)
-        w3 = torch.zeros(w.shape[0], w.shape[1], 3, 3, device=w.device)
-        w3[:, :, 1, 1] = w[:, :, 0, 0]
-        W["pq.w"], W["pq.b"] = _pack_direct(w3), f(P["post_quant_conv.bias"])
+        W = self._pack_common(P, ("post_quant_conv.weight", "decoder.conv_in.weight", "decoder.conv_out.weight"))
+        W["pq.w"], W["pq.b"] = self._pack_1x1_direct(P["post_quant_conv.weight"]), f(P["post_quant_conv.bias"])
         W["in.w"], W["in.b"] = _pack_direct(P["decoder.conv_in.weight"].detach()), f(P["decoder.conv_in.bias"])
         W["out.w"], W["out.b"] = _pack_direct(P["decoder.conv_out.weight"].detach()), f(P["decoder.conv_out.bias"])
-        for k in self.spec:
-            if k.endswith(".weight") and ".norm" in k:
-                W[k[:-7] + ".g"], W[k[:-7] + ".b"] = f(P[k]), f(P[k[:-6] + "bias"])
-        for k, shape in self.spec.items():
-            if not k.endswith(".weight") or len(shape) != 4 or k in ("post_quant_conv.weight", "decoder.conv_in.weight", "decoder.conv_out.weight"):
-                continue
-            base = k[:-7]
-            if shape[2] == 3:
-                W[base + ".w"] = mat(_conv3_matrix(P[k]), 9)
-            else:
-                W[base + ".w"] = mat(P[k].detach().reshape(shape[0], shape[1]))
-            W[base + ".b"] = f(P[base + ".bias"])
         self.W = W
 
     # ------------------------------------------------------------------------------------------ blocks
@@ -146,3 +197,48 @@ class VAEDecoderEngine:
         a = ops.groupnorm(h, W["decoder.norm_out.g"], W["decoder.norm_out.b"], 1e-6, True, out_f32=ops.act_dtype == F32)
         img = ops.conv3x3_direct(a, W["out.w"], W["out.b"], dd["out_ch"])
         return ops.nhwc_to_nchw(img)
+
+
+class VAEEncoderEngine(_VAEBlocks):
+    """`quant_conv(Encoder(x))` (autoencoder.py:352-357; model.py:763-880): conv_in, per level 2 ResnetBlocks (+ Downsample
+    = zero row/column appended at the far edges, then a stride-2 3x3 conv without padding), mid block, GroupNorm + swish +
+    conv_out -> the posterior's moments [F, 2 z_channels, h/8, w/8]; sampling the posterior is the caller's one-liner."""
+    _res = VAEDecoderEngine._res
+    _attn = VAEDecoderEngine._attn
+
+    def __init__(self, ddconfig: dict, ops, embed_dim: int = 4):
+        self.dd, self.ops, self.embed_dim = dict(ddconfig), ops, embed_dim
+        self.spec = encoder_param_spec(self.dd, embed_dim)
+        self.W = None
+
+    def pack(self, P: dict) -> None:
+        f = lambda t: t.detach().to(F32).contiguous()
+        W = self._pack_common(P, ("quant_conv.weight", "encoder.conv_in.weight"))
+        cin = self.dd["in_channels"]
+        W["in.w"], W["in.b"] = _pack_direct(P["encoder.conv_in.weight"].detach(), cin_pad=(cin + 3) // 4 * 4), f(P["encoder.conv_in.bias"])
+        W["q.w"], W["q.b"] = self._pack_1x1_direct(P["quant_conv.weight"]), f(P["quant_conv.bias"])
+        self.W = W
+
+    @torch.no_grad()
+    def encode_moments(self, x_nchw: torch.Tensor) -> torch.Tensor:
+        ops, W, dd = self.ops, self.W, self.dd
+        assert W is not None, "pack() the encoder parameters first"
+        ch_mult, nrb = tuple(dd["ch_mult"]), dd["num_res_blocks"]
+        Fr, cin, H, Wd = x_nchw.shape
+        xin = torch.zeros((Fr, H, Wd, W["in.w"].shape[1]), device=x_nchw.device, dtype=F32)     # channels padded to a multiple of 4
+        ops.nchw_to_nhwc(x_nchw.float().contiguous(), out=xin, ch_off=0)
+        h = ops.conv3x3_direct(xin, W["in.w"], W["in.b"], W["in.b"].numel())
+        for lvl in range(len(ch_mult)):
+            for i in range(nrb):
+                h = self._res(f"encoder.down.{lvl}.block.{i}", h)
+            if lvl != len(ch_mult) - 1:
+                k = f"encoder.down.{lvl}.downsample.conv"
+                cols, (f_, Ho, Wo) = ops.im2col_s2(h, pad=0)
+                h = ops.gemm(cols, W[k + ".w"], bias=W[k + ".b"]).view(f_, Ho, Wo, -1)
+        h = self._res("encoder.mid.block_1", h)
+        h = self._attn("encoder.mid.attn_1", h)
+        h = self._res("encoder.mid.block_2", h)
+        a = ops.groupnorm(h, W["encoder.norm_out.g"], W["encoder.norm_out.b"], 1e-6, True)
+        m = ops.gemm(a, W["encoder.conv_out.w"], bias=W["encoder.conv_out.b"], taps=(3, 3))
+        m = ops.conv3x3_direct(m.view(*h.shape[:-1], -1), W["q.w"], W["q.b"], W["q.b"].numel())
+        return ops.nhwc_to_nchw(m)

@@ -35,6 +35,12 @@ def test_conditioner_routing_matches_the_reference_rules():
     from torch.utils.data import DataLoader
     from panacea_b200.inference import SyntheticBEVDataset
     m = _engine()
+
+    class FakeFirstStage:                      # the routing is host logic; the native VAE encoder needs a GPU
+        def encode(self, x):
+            return torch.nn.functional.avg_pool2d(x, 8)[:, :1].repeat(1, 4, 1, 1)
+
+    m.conditioner.embedders[2].first_stage_model = FakeFirstStage()
     batch = next(iter(DataLoader(SyntheticBEVDataset(2, 4, (64, 128), use_last_frame=True), batch_size=1)))
     bu = dict(batch)
     bu["txt"] = ["" for _ in batch["txt"]]

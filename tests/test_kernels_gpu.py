@@ -213,6 +213,14 @@ def test_im2col_s2_matches_strided_conv(ops):
     ref = F.conv2d(x.to(torch.bfloat16).float().permute(0, 3, 1, 2), wp.float().reshape(N, 3, 3, C).permute(0, 3, 1, 2),
                    stride=2, padding=1).permute(0, 2, 3, 1)
     _close(out.reshape(Fr, Ho, Wo, N), ref, 2e-3, "im2col_s2 + gemm")
+    # pad = 0: the VAE encoder's Downsample (zero row / column appended at the far edges, stride-2 conv without padding)
+    cols0, (f, Ho0, Wo0) = ops.im2col_s2(x, pad=0)
+    out0 = ops.gemm(cols0, wp)
+    torch.cuda.synchronize()
+    xp = F.pad(x.to(torch.bfloat16).float().permute(0, 3, 1, 2), (0, 1, 0, 1))
+    ref0 = F.conv2d(xp, wp.float().reshape(N, 3, 3, C).permute(0, 3, 1, 2), stride=2, padding=0).permute(0, 2, 3, 1)
+    assert (Ho0, Wo0) == (H // 2, W // 2)
+    _close(out0.reshape(Fr, Ho0, Wo0, N), ref0, 2e-3, "im2col_s2(pad=0) + gemm")
 
 
 def test_layout_and_small_ops(ops):

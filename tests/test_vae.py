@@ -6,8 +6,8 @@ from pathlib import Path
 import pytest
 import torch
 
-from oracle.make_golden import VAE_DDCONFIG, vae_decoder_input, vae_decoder_weights
-from panacea_b200.vae import VAEDecoderEngine, decoder_param_spec
+from oracle.make_golden import VAE_DDCONFIG, vae_decoder_input, vae_decoder_weights, vae_encoder_input
+from panacea_b200.vae import VAEDecoderEngine, VAEEncoderEngine, decoder_param_spec, encoder_param_spec
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
 
@@ -20,6 +20,18 @@ def test_decoder_orchestration_matches_the_reference_on_cpu():
     eng.pack(vae_decoder_weights(eng.spec))
     out = eng.decode(vae_decoder_input())
     assert out.shape == g["image"].shape and (out - g["image"]).abs().max().item() < 5e-5
+
+
+def test_encoder_orchestration_matches_the_reference_on_cpu():
+    """quant_conv(Encoder(x)) (model.py:763-880; autoencoder.py:352-357), incl. the asymmetric (0,1,0,1) padding of the
+    stride-2 Downsample convs."""
+    from torch_ref_ops import TorchRefOps
+    g = torch.load(GOLDEN / "vae_decode_small.pt")
+    eng = VAEEncoderEngine(VAE_DDCONFIG, TorchRefOps())
+    assert sorted(eng.spec) == g["encoder_keys"]
+    eng.pack(vae_decoder_weights(eng.spec, seed=9))
+    out = eng.encode_moments(vae_encoder_input())
+    assert out.shape == g["moments"].shape and (out - g["moments"]).abs().max().item() < 5e-5
 
 
 def test_full_size_spec_is_the_sd_vae_decoder():
@@ -42,9 +54,10 @@ def test_mirror_first_stage_loads_reference_keys():
     res = m.load_state_dict(sd, strict=False)
     assert not [k for k in res.missing_keys if k.startswith(("decoder.", "post_quant_conv."))]
     assert torch.equal(m.state_dict()["decoder.conv_out.weight"], sd["decoder.conv_out.weight"])
-    assert m.encode(torch.zeros(2, 3, 32, 192)).shape == (2, 4, 8, 48)       # 2^(len(ch_mult)-1) = 4x here
     with pytest.raises(RuntimeError):
         m.decode(torch.zeros(2, 4, 8, 48))                    # no CPU path
+    with pytest.raises(RuntimeError):
+        m.encode(torch.zeros(2, 3, 32, 192))
 
 
 @pytest.mark.gpu
@@ -58,6 +71,24 @@ def test_decoder_on_gpu_matches_the_reference():
     rel = ((out - g["image"]).norm() / g["image"].norm()).item()
     print(f"PARITY vae_decode_small rel_l2 {rel:.3e}")
     assert out.shape == g["image"].shape and rel < 1.5e-2     # bf16 operands, fp32 accumulation / norms / residuals
+
+
+@pytest.mark.gpu
+def test_encoder_on_gpu_matches_the_reference():
+    from panacea_b200.sgm.models.autoencoder import AutoencoderKLInferenceWrapper
+    g = torch.load(GOLDEN / "vae_decode_small.pt")
+    m = AutoencoderKLInferenceWrapper(embed_dim=4, ddconfig=VAE_DDCONFIG, lossconfig={"target": "torch.nn.Identity"})
+    m.load_state_dict(vae_decoder_weights(encoder_param_spec(VAE_DDCONFIG, 4), seed=9), strict=False)
+    m = m.cuda()
+    mom = m.encode_moments(vae_encoder_input().cuda()).cpu()
+    rel = ((mom - g["moments"]).norm() / g["moments"].norm()).item()
+    print(f"PARITY vae_encode_small rel_l2 {rel:.3e}")
+    assert mom.shape == g["moments"].shape and rel < 1.5e-2
+    torch.manual_seed(0)
+    z = m.encode(vae_encoder_input().cuda())
+    assert z.shape == (2, 4, 8, 48) and torch.isfinite(z).all()
+    m.sample_posterior = False
+    assert torch.equal(m.encode(vae_encoder_input().cuda()).cpu(), mom[:, :4])
 
 
 @pytest.mark.gpu

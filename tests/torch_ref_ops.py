@@ -154,10 +154,14 @@ class TorchRefOps:
             y = y + addend
         return y.contiguous().to(out_dtype)
 
-    def im2col_s2(self, x):
+    def im2col_s2(self, x, pad=1):
         Fr, H, W, C = x.shape
-        Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
-        xp = F.pad(x, (0, 0, 1, 1, 1, 1))
+        if pad == 1:
+            Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+            xp = F.pad(x, (0, 0, 1, 1, 1, 1))
+        else:
+            Ho, Wo = (H - 2) // 2 + 1, (W - 2) // 2 + 1
+            xp = F.pad(x, (0, 0, 0, 2, 0, 2))
         cols = torch.stack([xp[:, i:i + 2 * Ho:2, j:j + 2 * Wo:2, :] for i in range(3) for j in range(3)], dim=3)
         return cols.reshape(Fr * Ho * Wo, 9 * C), (Fr, Ho, Wo)
 
@@ -262,8 +266,8 @@ class TorchSplitOps(TorchRefOps):
     def attention_temporal(self, *a, **k):
         return _enc(super().attention_temporal(*a, **k))
 
-    def im2col_s2(self, x):
-        cols, geo = super().im2col_s2(x)
+    def im2col_s2(self, x, pad=1):
+        cols, geo = super().im2col_s2(x, pad)
         C = x.shape[-1]
         return _enc(cols.reshape(cols.shape[0], 9, C)).reshape(cols.shape[0], 27 * C), geo
 
