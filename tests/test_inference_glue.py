@@ -36,7 +36,7 @@ def test_conditioner_routing_matches_the_reference_rules():
     from panacea_b200.inference import SyntheticBEVDataset
     m = _engine()
 
-    class FakeFirstStage:                      # the routing is host logic; the native VAE encoder needs a GPU
+    class FakeFirstStage(torch.nn.Module):     # the routing is host logic; the native VAE encoder needs a GPU
         def encode(self, x):
             return torch.nn.functional.avg_pool2d(x, 8)[:, :1].repeat(1, 4, 1, 1)
 
