@@ -373,7 +373,7 @@ def run_ours(args) -> None:
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         log("CPU baseline (oracle port) ...")
-        val, desc, cores, msc = cpu_baseline(float(os.environ.get("PN_CPU_BUDGET_S", "60")))
+        val, desc, cores, msc = cpu_baseline(float(os.environ.get("PN_CPU_BUDGET_S", "180")))    # same samples as --impl reference when they fit
         log(f"CPU baseline: {val:.5f} steps/s on {cores} cores")
         cpu = {"value": val, "unit": "steps/s", "cores": cores, "kind": "port", "sample": desc, "sample_seconds": msc}
 
