@@ -76,7 +76,7 @@ typedef struct pn_gemm_args {
   /* LayerNorm folded into the GEMMs around the bf16 token stream (attention.py:699-701 + :726-747, norm1/2/3):
    * ln_stats_out — this GEMM (1x1, K <= 640, bf16 out) also writes, per output row, pn_gemm_ln_parts(N) partial
    *   (sum, sum of squares) pairs of the bf16 values it stores: float [rows][parts][2];
-   * ln_stats_in / ln_parts_in / ln_colsum / ln_eps — A is the UN-normalised stream, B = W diag(gamma); the epilogue
+   * ln_stats_in / ln_parts_in / ln_colsum / ln_eps — (1x1, K <= 640, bf16 out, no GEGLU) A is the UN-normalised stream, B = W diag(gamma); the epilogue
    *   finishes the LayerNorm: out = rstd_m (acc - mean_m s_n) + bias_n with s_n = ln_colsum[n] = sum_k B[n,k] and the
    *   caller's bias_n = sum_k beta_k W[n,k] (+ the layer's own bias); mean/rstd over the C = K channels of row m. */
   const float* ln_stats_in;

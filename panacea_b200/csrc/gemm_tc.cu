@@ -27,7 +27,11 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle atom row
 // warp 0 TMA, warp 1 MMA, warps 2.. epilogue: 8 warps for the fp32/residual mode (168 registers each), 12 for the
 // ALU-heavy bf16 / GEGLU modes (the register file is granted per 4-warp group: 16 warps x 128 registers)
-constexpr bool gemm_streaming(int mode) { return mode == 4 || mode == 5; }
+// streaming epilogues: 4 = fp32, 5 = bf16, 7 = bf16 that also emits the rows' (sum, sum of squares) — a PRODUCER of the
+// bf16 token stream —, 8 = bf16 whose A operand is the un-normalised token stream: it finishes a folded LayerNorm in the
+// epilogue (a CONSUMER). 7 and 8 are separate instantiations so that the plain kernels carry none of their code.
+constexpr bool gemm_streaming(int mode) { return mode == 4 || mode == 5 || mode == 7 || mode == 8; }
+constexpr bool gemm_stream_bf16(int mode) { return mode == 5 || mode == 7 || mode == 8; }
 constexpr int gemm_threads(int mode) { return (mode == 0 || mode == 3 || mode == 6) ? 320 : gemm_streaming(mode) ? 352 : mode == 2 ? 576 : 448; }
 
 struct GemmParams {
@@ -80,14 +84,14 @@ struct GemmSmem {
   static constexpr int HALO_STAGES = 3;
   static constexpr int A_HALO_BYTES = 23552;             // 18*10*128 = 23040, padded to a multiple of 1024
   static constexpr int A_HALO_TX = 18 * 10 * 128;
-  static constexpr int RCHUNK_BYTES = MODE == 5 ? 128 * 64 : 128 * 128;              // 128 rows x 32 (bf16 | fp32)
+  static constexpr int RCHUNK_BYTES = gemm_stream_bf16(MODE) ? 128 * 64 : 128 * 128;              // 128 rows x 32 (bf16 | fp32)
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / NCTA) * BK * 2;   // a CTA pair splits the N tile: each CTA stages BN/2 weight rows
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int RING_BYTES = MODE == 6 ? HALO_STAGES * A_HALO_BYTES + STAGES * B_BYTES : STAGES * STAGE_BYTES;
   static constexpr int STAGING_BYTES = gemm_streaming(MODE) ? (BN / 32) * RCHUNK_BYTES : NEPI * STAGE_WARP_BYTES;
   static constexpr bool BIAS_SMEM = (MODE == 1 || MODE == 2);    // the ALU-bound epilogues stage their bias slice in smem
-  static constexpr int ROWMAP_BYTES = gemm_streaming(MODE) ? 0 : NEPI * 32 * 4 + (BIAS_SMEM ? NEPI * 512 : 0) + (MODE == 2 ? NEPI * 512 : 0);
+  static constexpr int ROWMAP_BYTES = gemm_streaming(MODE) ? 0 : NEPI * 32 * 4 + (BIAS_SMEM ? NEPI * 512 : 0);
   static constexpr int BAR_BYTES = (2 * STAGES + 4 + 2 * (BN / 32) + 8) * 8 + 16;
   static constexpr int TOTAL = RING_BYTES + STAGING_BYTES + ROWMAP_BYTES + BAR_BYTES + 1024;
 };
@@ -529,7 +533,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
       const int n_base = tcol * BN;
       const bool row_ok = grow < (long long)p.NB * p.H * p.W;
       float ln_mu = 0.f, ln_rstd = 1.f;
-      if (MODE == 5 && p.ln_stats_in != nullptr && row_ok) {      // finish the LayerNorm statistics of this thread's row
+      if (MODE == 8 && row_ok) {      // finish the LayerNorm statistics of this thread's row
         float sm = 0.f, sq = 0.f;
         const float2* st = reinterpret_cast<const float2*>(p.ln_stats_in) + grow * p.ln_parts_in;
         for (int q = 0; q < p.ln_parts_in; ++q) { const float2 t2 = __ldg(st + q); sm += t2.x; sq += t2.y; }
@@ -537,13 +541,29 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
         ln_rstd = rsqrtf(fmaxf(sq * p.ln_inv_dim - ln_mu * ln_mu, 0.f) + p.ln_eps);
       }
       f32x2 st_sum2 = 0ull, st_sq2 = 0ull;                        // partial row sums of what this thread stores (producer)
-      { const long long w0 = dbg ? clock64() : 0; mbar_wait(&tmem_full[acc], acc_phase); if (dbg) d_tf += clock64() - w0; }
-      tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t(lane_grp * 32) << 16) + acc * BN;
 #pragma unroll
       for (int k = 0; k < MYCH; ++k) {
         const int c = half + 2 * k;
         if (c < NCH) {
+          // column vectors of this chunk (bias / folded-LayerNorm s_n): they do not depend on the accumulator, so they are
+          // requested BEFORE the wait for it — behind tcgen05.wait::ld their L2 round trip sat on the per-tile critical
+          // path of these latency-bound short-K tiles
+          const int n0 = n_base + c * 32;
+          float4 bq[8], sq4[8];
+          constexpr bool use_ln = MODE == 8;
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bq[j] = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 4 * j));
+          }
+          if (use_ln) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sq4[j] = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + n0 + 4 * j));
+          }
+          if (k == 0) {
+            { const long long w0 = dbg ? clock64() : 0; mbar_wait(&tmem_full[acc], acc_phase); if (dbg) d_tf += clock64() - w0; }
+            tc_fence_after();
+          }
           uint32_t v[32];
           tmem_ld_32x32(t_row + c * 32, v);
           tmem_ld_wait();
@@ -555,24 +575,22 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
               else mbar_arrive(&tmem_empty[acc]);
             }
           }
-          const int n0 = n_base + c * 32;
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (MODE == 5 && p.ln_stats_in != nullptr) {
+          if (use_ln) {
             // out = rstd * acc + (-rstd * mean) * s_n + t_n : two packed FMAs per pair, bias (= t_n) included
             const f32x2 a2 = f2_splat(ln_rstd), b2 = f2_splat(-ln_rstd * ln_mu);
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + n0 + j));
-              const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+              const float4 s4 = sq4[j >> 2], t4 = bq[j >> 2];
               f2_unpack(f2_fma(a2, f2_pack(f[j], f[j + 1]), f2_fma(b2, f2_pack(s4.x, s4.y), f2_pack(t4.x, t4.y))), f[j], f[j + 1]);
               f2_unpack(f2_fma(a2, f2_pack(f[j + 2], f[j + 3]), f2_fma(b2, f2_pack(s4.z, s4.w), f2_pack(t4.z, t4.w))), f[j + 2], f[j + 3]);
             }
           } else if (p.bias != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+              const float4 b4 = bq[j >> 2];
               f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
             }
           }
@@ -586,7 +604,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
           }
           { const long long w0 = dbg ? clock64() : 0; mbar_wait(&r_full[c], (uint32_t)(it & 1)); if (dbg) d_rf += clock64() - w0; }
           if (dbgmode == 3) {
-          } else if (MODE == 5) {
+          } else if (gemm_stream_bf16(MODE)) {
             // 32 bf16 = 64 B per row; TMA SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3
             uint8_t* rowp = staging + c * S::RCHUNK_BYTES + r * 64;
 #pragma unroll
@@ -604,7 +622,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
               const uint4 o4 = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
                                           pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
               *q = o4;
-              if (p.ln_stats_out != nullptr) {           // row sums of the fp32 values (their bf16 rounding, which the
+              if (MODE == 7) {                           // row sums of the fp32 values (their bf16 rounding, which the
 #pragma unroll                                           // consumer's MMA reads, perturbs mean / variance by < 2^-9 / sqrt(C))
                 for (int e = 0; e < 8; e += 2) {
                   const f32x2 pr = f2_pack(f[8 * j + e], f[8 * j + e + 1]);
@@ -631,7 +649,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
           if (lane == 0) mbar_arrive(&c_ready[c]);
         }
       }
-      if (MODE == 5 && p.ln_stats_out != nullptr && row_ok) {
+      if (MODE == 7 && row_ok) {
         float s0, s1, q0, q1;
         f2_unpack(st_sum2, s0, s1);
         f2_unpack(st_sq2, q0, q1);
@@ -653,7 +671,6 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
     uint8_t* my_stage = staging + ew * S::STAGE_WARP_BYTES;
     int* my_rowmap = rowmap + ew * 32;
     float* my_bias = reinterpret_cast<float*>(rowmap + NEPI * 32) + ew * 128;   // bias of this warp's <= 4 chunks
-    float* my_colsum = reinterpret_cast<float*>(rowmap + NEPI * 32) + NEPI * 128 + ew * 128;   // MODE 2: folded-LayerNorm s_n
     constexpr int NCH = BN / 32;
     constexpr int MYCH = (NCH + EG - 1) / EG;
     constexpr int PRECH = MYCH < 2 ? MYCH : 2;   // chunks whose residual is prefetched at tile start (register budget:
@@ -692,23 +709,8 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
           my_bias[k * 32 + lane] = (half + EG * k < NCH && n < p.N) ? __ldg(p.bias + n) : 0.f;
         }
       }
-      if (MODE == 2 && p.ln_stats_in != nullptr) {
-#pragma unroll
-        for (int k = 0; k < MYCH; ++k) {
-          const int n = n_base + (half + EG * k) * 32 + lane;
-          my_colsum[k * 32 + lane] = (half + EG * k < NCH && n < p.N) ? __ldg(p.ln_colsum + n) : 0.f;
-        }
-      }
       __syncwarp();
       const int my_row = my_rowmap[lane];
-      float ln_mu = 0.f, ln_rstd = 1.f;
-      if (MODE == 2 && p.ln_stats_in != nullptr && my_row >= 0) {
-        float sm = 0.f, sq = 0.f;
-        const float2* st = reinterpret_cast<const float2*>(p.ln_stats_in) + (long long)my_row * p.ln_parts_in;
-        for (int q = 0; q < p.ln_parts_in; ++q) { const float2 t2 = __ldg(st + q); sm += t2.x; sq += t2.y; }
-        ln_mu = sm * p.ln_inv_dim;
-        ln_rstd = rsqrtf(fmaxf(sq * p.ln_inv_dim - ln_mu * ln_mu, 0.f) + p.ln_eps);
-      }
       // ---- residual prefetch (fp32 output path): lane -> (row i*4 + lane/8, 16-byte column chunk lane%8)
       float4 rpre[PRECH][8];
       const bool pre = (MODE == 0 || MODE == 3) && (p.residual != nullptr);
@@ -751,16 +753,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (MODE == 2 && p.ln_stats_in != nullptr) {
-            const f32x2 a2 = f2_splat(ln_rstd), b2 = f2_splat(-ln_rstd * ln_mu);
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 s4 = *reinterpret_cast<const float4*>(my_colsum + k * 32 + j);
-              const float4 t4 = *reinterpret_cast<const float4*>(my_bias + k * 32 + j);
-              f2_unpack(f2_fma(a2, f2_pack(f[j], f[j + 1]), f2_fma(b2, f2_pack(s4.x, s4.y), f2_pack(t4.x, t4.y))), f[j], f[j + 1]);
-              f2_unpack(f2_fma(a2, f2_pack(f[j + 2], f[j + 3]), f2_fma(b2, f2_pack(s4.z, s4.w), f2_pack(t4.z, t4.w))), f[j + 2], f[j + 3]);
-            }
-          } else if (p.bias != nullptr) {
+          if (p.bias != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1031,7 +1024,7 @@ extern "C" int pn_gemm(const pn_gemm_args* a, void* stream_v) {
   if (a->residual2) PN_REQUIRE(!a->out_bf16 && !a->geglu && a->ldr2 >= a->N && a->ldr2 % 4 == 0, "pn_gemm: residual2 needs fp32 out and a valid ldr2");
   if (a->rowvec) PN_REQUIRE(a->rows_per_group > 0 && a->n_groups > 0, "pn_gemm: rowvec needs rows_per_group/n_groups");
   if (a->ln_stats_in) PN_REQUIRE(a->bias != nullptr, "pn_gemm: a folded LayerNorm needs bias = W beta (+ bias)");
-  if (a->ln_stats_in) PN_REQUIRE(a->ln_colsum && a->ln_parts_in > 0 && a->ln_parts_in <= 64 && a->out_bf16 && a->taps_h == 1 && a->taps_w == 1,
+  if (a->ln_stats_in) PN_REQUIRE(a->ln_colsum && a->ln_parts_in > 0 && a->ln_parts_in <= 64 && a->out_bf16 && !a->geglu && a->taps_h == 1 && a->taps_w == 1,
                                  "pn_gemm: a folded LayerNorm needs ln_colsum, 1..64 partial sums per row, a 1x1 GEMM and bf16 output");
 
   GemmParams p;
@@ -1132,7 +1125,8 @@ extern "C" int pn_gemm(const pn_gemm_args* a, void* stream_v) {
     PN_REQUIRE(stream_mode && a->out_bf16, "pn_gemm: ln_stats_out needs the streaming bf16 epilogue (1x1 GEMM, K <= 640, bf16 out, N %% 160 or 128 == 0)");
     p.ln_parts_out = 2 * p.tiles_col;
   }
-  if (a->ln_stats_in) PN_REQUIRE(a->geglu || (stream_mode && a->out_bf16), "pn_gemm: a folded LayerNorm needs the GEGLU or the streaming bf16 epilogue");
+  if (a->ln_stats_in) PN_REQUIRE(stream_mode && a->out_bf16 && a->ln_stats_out == nullptr,
+                                 "pn_gemm: a folded LayerNorm needs the streaming bf16 epilogue (1x1 GEMM, K <= 640) and cannot also emit row sums");
   // weight-stationary schedule: 1x1 GEMMs with K = 320 (5 k-blocks, every ring has >= 5 stages) and enough column
   // tiles and row tiles for the saved weight traffic to matter
   p.bstat = (gemm_bstat_enabled() && !halo_mode && a->taps_h == 1 && a->taps_w == 1 && a->C == 5 * BK && p.tiles_col >= 3 &&
@@ -1153,8 +1147,15 @@ extern "C" int pn_gemm(const pn_gemm_args* a, void* stream_v) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
   if (halo_mode) return NCTA == 2 ? launch_gemm_mode<160, 10, 2, 6>(p, stream) : launch_gemm_mode<160, 5, 1, 6>(p, stream);
   if (stream_mode && a->out_bf16) {
-    if (NCTA == 2) return BN == 160 ? launch_gemm_mode<160, 6, 2, 5>(p, stream) : launch_gemm_mode<128, 7, 2, 5>(p, stream);
-    return BN == 160 ? launch_gemm_mode<160, 5, 1, 5>(p, stream) : launch_gemm_mode<128, 6, 1, 5>(p, stream);
+#define PN_STREAM_BF16(M)                                                                                                   \
+    do {                                                                                                                    \
+      if (NCTA == 2) return BN == 160 ? launch_gemm_mode<160, 6, 2, M>(p, stream) : launch_gemm_mode<128, 7, 2, M>(p, stream); \
+      return BN == 160 ? launch_gemm_mode<160, 5, 1, M>(p, stream) : launch_gemm_mode<128, 6, 1, M>(p, stream);             \
+    } while (0)
+    if (a->ln_stats_in) PN_STREAM_BF16(8);
+    if (a->ln_stats_out) PN_STREAM_BF16(7);
+    PN_STREAM_BF16(5);
+#undef PN_STREAM_BF16
   }
   if (stream_mode) {
     if (NCTA == 2) return BN == 160 ? launch_gemm_mode<160, 5, 2, 4>(p, stream) : launch_gemm_mode<128, 6, 2, 4>(p, stream);

@@ -128,12 +128,8 @@ class Engine:
                         W[f"{t}.{a}.o.b"] = f(P[f"{t}.{a}.to_out.0.bias"])
                     # GEGLU: 16 value rows then their 16 gate rows, so one accumulator chunk holds both halves
                     w1, b1 = P[t + ".ff.net.0.proj.weight"].detach(), P[t + ".ff.net.0.proj.bias"].detach()
-                    if fold and getattr(self.ops, "fold_layernorm_ff1", False):
-                        wf, sf, tf = self._ln_fold_pack(w1, b1, W[t + ".norm3.g"], W[t + ".norm3.b"], pack=geglu_pack)
-                        W[t + ".ff1.w"], W[t + ".ff1.s"], W[t + ".ff1.b"] = wf, sf, tf
-                    else:
-                        W[t + ".ff1.w"] = mat(geglu_pack(w1))
-                        W[t + ".ff1.b"] = geglu_pack(b1).to(F32).contiguous()
+                    W[t + ".ff1.w"] = mat(geglu_pack(w1))
+                    W[t + ".ff1.b"] = geglu_pack(b1).to(F32).contiguous()
                     W[t + ".ff2.w"] = mat(P[t + ".ff.net.2.weight"]); W[t + ".ff2.b"] = f(P[t + ".ff.net.2.bias"])
             elif st.kind == "down":
                 W[k + ".w"] = mat(_conv3_matrix(P[k + ".op.weight"]), 9); W[k + ".b"] = f(P[k + ".op.bias"])
@@ -321,15 +317,11 @@ class Engine:
         y, st = ops.gemm(o.view(-1, C), W[t + ".attn1.o.w"], bias=W[t + ".attn1.o.b"], residual=y, out=y, out_dtype=y.dtype, ln_stats_out=True)
         q = ops.gemm(y, W[t + ".q2.w"], bias=W[t + ".q2.t"], out_dtype=dt, ln=(st, W[t + ".q2.s"], eps))
         o = ops.attention_text(q.view(b, T * H * Wd, C), kv, heads)
-        if (t + ".ff1.s") in W:
-            y, st = ops.gemm(o.view(-1, C), W[t + ".attn2.o.w"], bias=W[t + ".attn2.o.b"], residual=y, out=y, out_dtype=y.dtype, ln_stats_out=True)
-            ff = ops.gemm(y, W[t + ".ff1.w"], bias=W[t + ".ff1.b"], geglu=True, out_dtype=ops.act_dtype, ln=(st, W[t + ".ff1.s"], eps))
-        else:
-            # norm3 stays a kernel: the GEGLU epilogue is the long pole of ff1 at level 0 and the rank-1 correction costs it
-            # more (+2.7 ms per step) than the LayerNorm pass it would save (1.8 ms) — measured, profiles/README.md
-            y = ops.gemm(o.view(-1, C), W[t + ".attn2.o.w"], bias=W[t + ".attn2.o.b"], residual=y, out=y, out_dtype=y.dtype)
-            n3 = ops.layernorm(y, W[t + ".norm3.g"], W[t + ".norm3.b"])
-            ff = ops.gemm(n3, W[t + ".ff1.w"], bias=W[t + ".ff1.b"], geglu=True, out_dtype=ops.act_dtype)
+        # norm3 stays a kernel: the GEGLU epilogue is the long pole of ff1 at level 0 and a rank-1 correction there cost it
+        # more (+2.7 ms per step) than the LayerNorm pass it saved (1.8 ms) — measured in round 2, profiles/README.md
+        y = ops.gemm(o.view(-1, C), W[t + ".attn2.o.w"], bias=W[t + ".attn2.o.b"], residual=y, out=y, out_dtype=y.dtype)
+        n3 = ops.layernorm(y, W[t + ".norm3.g"], W[t + ".norm3.b"])
+        ff = ops.gemm(n3, W[t + ".ff1.w"], bias=W[t + ".ff1.b"], geglu=True, out_dtype=ops.act_dtype)
         return ops.gemm(ff, W[t + ".ff2.w"], bias=W[t + ".ff2.b"], residual=y, out_dtype=torch.bfloat16)
 
     def _stt(self, W, st: Stage, x):

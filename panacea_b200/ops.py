@@ -63,7 +63,6 @@ class NativeOps:
     token_dtype = BF16        # token stream inside a transformer block (proj_in .. proj_out): 3 residual adds per block
     fold_layernorm = True     # LayerNorm folded into the GEMMs around the bf16 token stream (C <= LN_FOLD_MAX_C)
     LN_FOLD_MAX_C = 640       # the producers' streaming bf16 epilogue (which emits the row sums) covers K <= 640
-    fold_layernorm_ff1 = False  # norm3 -> GEGLU: supported and tested, but a net loss on B200 (the GEGLU epilogue is the long pole)
 
     def __init__(self):
         import os
@@ -74,8 +73,6 @@ class NativeOps:
             self.token_dtype = F32
         if os.environ.get("PN_LN_FOLD") == "0" or self.token_dtype != BF16:              # A/B measurement of the LayerNorm fold
             self.fold_layernorm = False
-        if os.environ.get("PN_LN_FOLD_FF1") == "1":
-            self.fold_layernorm_ff1 = True
 
     def pack_matrix(self, w: torch.Tensor, taps: int = 1) -> torch.Tensor:
         """fp32 weight [N, taps*C] -> the B operand pn_gemm reads in this op set's precision mode."""

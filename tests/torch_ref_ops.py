@@ -219,7 +219,6 @@ class TorchFoldOps(TorchRefOps):
     """TorchRefOps with the LayerNorm fold switched on (the NativeOps fast-path orchestration: row statistics from the
     producers of the token stream, W diag(gamma) / column sums / W beta in the consumers), fp32 stream on CPU."""
     fold_layernorm = True
-    fold_layernorm_ff1 = True
     LN_FOLD_MAX_C = 640
 
 
