@@ -309,6 +309,72 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const TIn* __restrict__ 
   }
 }
 
+// bf16 token stream -> bf16 operand, the LayerNorm of the fast path (norm3 of every block, all three at C = 1280):
+// LPR lanes per row, NV 16-byte loads (8 channels each) per lane all in flight at once, ONE shuffle reduction of
+// (sum, sum of squares) over the LPR lanes — the warp-per-row two-reduction kernel above was latency-bound at 37 % of the
+// HBM bandwidth for this 2-bytes-in / 2-bytes-out shape.
+template <int LPR, int NV>
+__global__ void __launch_bounds__(256) layernorm_bf16_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
+                                                             long long rows, int C, float eps) {
+  pdl_prologue_done();
+  constexpr int RPW = 32 / LPR;                                  // rows per warp and pass
+  const int lane = threadIdx.x & 31, sub = lane % LPR;
+  // the affine parameters are staged in shared memory once per CTA (re-reading them from global per row cost four times
+  // the row's own bytes in L1 traffic); each CTA then walks many rows
+  extern __shared__ float ln_gb[];                               // [2][C]
+  for (int i = threadIdx.x; i < C / 4; i += blockDim.x) {
+    reinterpret_cast<float4*>(ln_gb)[i] = reinterpret_cast<const float4*>(gamma)[i];
+    reinterpret_cast<float4*>(ln_gb + C)[i] = reinterpret_cast<const float4*>(beta)[i];
+  }
+  __syncthreads();
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const float inv_c = 1.f / (float)C;
+  for (long long base = warp0 * RPW; base < rows; base += nwarps * RPW) {
+    const long long row = base + lane / LPR;
+    const bool ok = row < rows;
+    const __nv_bfloat16* xr = x + (ok ? row : base) * C;
+    uint4 raw[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) raw[i] = *reinterpret_cast<const uint4*>(xr + (sub + i * LPR) * 8);
+    float v[NV][8];
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const uint32_t w[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        v[i][2 * e] = __uint_as_float(w[e] << 16);
+        v[i][2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+        s += v[i][2 * e] + v[i][2 * e + 1];
+        q = fmaf(v[i][2 * e], v[i][2 * e], fmaf(v[i][2 * e + 1], v[i][2 * e + 1], q));
+      }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    const float mean = s * inv_c;
+    const float rstd = rsqrtf(fmaxf(q * inv_c - mean * mean, 0.f) + eps);
+    if (ok) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c0 = (sub + i * LPR) * 8;
+        const float4 g0 = *reinterpret_cast<const float4*>(ln_gb + c0), g1 = *reinterpret_cast<const float4*>(ln_gb + c0 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(ln_gb + C + c0), b1 = *reinterpret_cast<const float4*>(ln_gb + C + c0 + 4);
+        const float gq[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bq[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = (v[i][e] - mean) * rstd * gq[e] + bq[e];
+        *reinterpret_cast<uint4*>(y + row * C + (sub + i * LPR) * 8) =
+            make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+      }
+    }
+  }
+}
+
 }  // namespace pn
 
 using namespace pn;
@@ -431,8 +497,30 @@ extern "C" int pn_layernorm(const void* x, int x_is_bf16, const float* gamma, co
   PN_REQUIRE(rows > 0, "pn_layernorm: empty input");
   PN_REQUIRE(operand_mode >= 0 && operand_mode <= 2, "pn_layernorm: operand_mode %d", operand_mode);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
-  const long long blocks = (rows * 32 + 255) / 256;
   const int C = (int)channels;
+  if (x_is_bf16 && operand_mode == PN_OP_BF16 && C % 64 == 0) {
+    // fast path: LPR lanes per row, NV = C / (8 LPR) loads per lane (5 for C = 320 / 640 / 1280)
+#define PN_LNB(LPR, NV)                                                                                                            \
+    do {                                                                                                                            \
+      const long long rows_per_block = 8 * (32 / LPR);                                                                              \
+      long long nb = (rows + rows_per_block - 1) / rows_per_block;                                                                  \
+      if (nb > 6ll * sm_count()) nb = 6ll * sm_count();          /* grid-stride over the rows: affine parameters staged once per CTA */ \
+      launch_kernel(layernorm_bf16_kernel<LPR, NV>, dim3((unsigned)nb), dim3(256), (size_t)C * 8, st, 1, reinterpret_cast<const __nv_bfloat16*>(x), \
+                    gamma, beta, reinterpret_cast<__nv_bfloat16*>(y), (long long)rows, C, eps);                                     \
+      PN_CHECK_CUDA(cudaGetLastError());                                                                                            \
+      return PN_OK;                                                                                                                 \
+    } while (0)
+    for (int lpr = 8; lpr <= 32; lpr *= 2) {
+      if (C % (8 * lpr) != 0) continue;
+      const int nv = C / (8 * lpr);
+      if (nv < 1 || nv > 8) continue;
+      if (lpr == 8) { switch (nv) { case 1: PN_LNB(8, 1); case 2: PN_LNB(8, 2); case 3: PN_LNB(8, 3); case 4: PN_LNB(8, 4); case 5: PN_LNB(8, 5); case 6: PN_LNB(8, 6); case 7: PN_LNB(8, 7); default: PN_LNB(8, 8); } }
+      if (lpr == 16) { switch (nv) { case 1: PN_LNB(16, 1); case 2: PN_LNB(16, 2); case 3: PN_LNB(16, 3); case 4: PN_LNB(16, 4); case 5: PN_LNB(16, 5); case 6: PN_LNB(16, 6); case 7: PN_LNB(16, 7); default: PN_LNB(16, 8); } }
+      switch (nv) { case 1: PN_LNB(32, 1); case 2: PN_LNB(32, 2); case 3: PN_LNB(32, 3); case 4: PN_LNB(32, 4); case 5: PN_LNB(32, 5); case 6: PN_LNB(32, 6); case 7: PN_LNB(32, 7); default: PN_LNB(32, 8); }
+    }
+#undef PN_LNB
+  }
+  const long long blocks = (rows * 32 + 255) / 256;
 #define PN_LN(MAXV)                                                                                                          \
   do {                                                                                                                      \
     if (x_is_bf16)                                                                                                          \
