@@ -98,7 +98,7 @@ def _view_ref(qkv, heads, cross):
 
 
 @pytest.mark.parametrize("Fr,H,w,heads", [(2, 8, 16, 1), (1, 32, 56, 5), (2, 16, 28, 2), (2, 8, 14, 3), (3, 4, 7, 2),
-                                          (1, 32, 64, 2), (2, 2, 3, 1), (1, 1, 2, 1), (2, 16, 24, 2)])
+                                          (1, 32, 64, 2), (2, 2, 3, 1), (1, 1, 2, 1), (2, 16, 24, 2), (2, 12, 28, 2), (1, 20, 28, 1)])
 @pytest.mark.parametrize("cross", [False, True])
 def test_attention_view(ops, Fr, H, w, heads, cross):
     C = heads * 64
@@ -108,7 +108,7 @@ def test_attention_view(ops, Fr, H, w, heads, cross):
     _close(out, _view_ref(qkv, heads, cross), 2e-2, f"attention_view cross={cross}")
 
 
-@pytest.mark.parametrize("Fr,H,w,heads", [(1, 32, 56, 4), (2, 16, 28, 2), (2, 8, 14, 3), (1, 32, 64, 2), (2, 2, 3, 1), (2, 16, 24, 2)])
+@pytest.mark.parametrize("Fr,H,w,heads", [(1, 32, 56, 4), (2, 16, 28, 2), (2, 8, 14, 3), (1, 32, 64, 2), (2, 2, 3, 1), (2, 16, 24, 2), (2, 12, 28, 2), (1, 20, 28, 1)])
 @pytest.mark.parametrize("cross", [False, True])
 def test_attention_view_head_dim_80(ops, Fr, H, w, heads, cross):
     """BASELINE.json configs[4]: head_dim 80 = a 64-channel tile + a 16-channel tile per Q/K/V (fifth K step of S, second
