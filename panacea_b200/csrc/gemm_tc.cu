@@ -42,7 +42,8 @@ struct GemmParams {
   int has_res;
 #ifdef PN_GEMM_ROLE_TIMERS
   int debug;                   // diagnostics builds only — PN_GEMM_DEBUG timing experiments: 1 = no TMA loads after the first
-                               // ring fill, 2 = no MMA issue, 3 = epilogue reads TMEM only, 4 = no global stores, 5 = role timers
+                               // ring fill, 2 = no MMA issue, 3 = epilogue reads TMEM only, 4 = no global stores, 5 = role timers,
+                               // 6 = 2 + 3 (loads only), 7 = 1 + 3 (MMAs only); +8 = the experiment with the role timers on
 #endif
   // geometry of the A tensor / output rows
   int NB, H, W;
@@ -145,9 +146,11 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 #ifdef PN_GEMM_ROLE_TIMERS
-  const int dbgmode = p.debug;
+  const int dbgmode = p.debug & 7;      // the experiment
+  const bool dbgtime = (p.debug & 8) != 0 || (p.debug & 7) == 5;   // role timers of CTA 0 (5 = timers alone, 8+n = experiment n timed)
 #else
   constexpr int dbgmode = 0;
+  constexpr bool dbgtime = false;
 #endif
   // NCTA == 2: the two CTAs of a cluster form a UMMA pair (cta_group::2). Each CTA owns 128 rows of a 256-row
   // tile (its own A stage and TMEM lanes) and stages half of the N tile's weight rows; the leader (rank 0)
@@ -329,7 +332,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
     bool first = true;
     int cur_col = -1;
     uint32_t bgen = 0;                            // weight-stationary: weight tiles loaded so far
-    const bool dbg = kRoleTimers && dbgmode == 5 && blockIdx.x == 0;
+    const bool dbg = kRoleTimers && dbgtime && blockIdx.x == 0;
     long long d_t0 = dbg ? clock64() : 0, d_wait = 0;
     for (int ti = 0, tile = t_begin; ti < t_count; ++ti, tile += t_step) {
       const int tcol = tile_col(tile);
@@ -359,7 +362,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
       }
       int kc = 0, dx = -p.pad_w, dy = -p.pad_h;   // k-block -> (tap row, tap column, channel chunk), kept incrementally
       for (int kb = 0; kb < num_k_blocks; ++kb) {
-        if (!(dbgmode == 1 && !(first && kb < STAGES))) {   // experiment 1: the ring is filled once, never again
+        if (!((dbgmode == 1 || dbgmode == 7) && !(first && kb < STAGES))) {   // experiment 1: the ring is filled once, never again
           { const long long w0 = dbg ? clock64() : 0; mbar_wait(&empty_bar[stage], phase ^ 1); if (dbg) d_wait += clock64() - w0; }
           if (elect_one()) {
             uint8_t* sA = stage_base + stage * S::STAGE_BYTES;
@@ -402,7 +405,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
       bool first = true;
       int cur_col = -1;
       uint32_t bgen = 0;
-      const bool dbg = kRoleTimers && dbgmode == 5 && blockIdx.x == 0;
+      const bool dbg = kRoleTimers && dbgtime && blockIdx.x == 0;
       long long d_t0 = dbg ? clock64() : 0, d_acc = 0, d_full = 0;
       for (int ti = 0, tile = t_begin; ti < t_count; ++ti, tile += t_step) {
         const bool bstat = MODE != 6 && p.bstat;
@@ -415,14 +418,14 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           const long long w1 = dbg ? clock64() : 0;
-          if (!(dbgmode == 1 && !(first && kb < STAGES))) mbar_wait(&full_bar[stage], phase);
+          if (!((dbgmode == 1 || dbgmode == 7) && !(first && kb < STAGES))) mbar_wait(&full_bar[stage], phase);
           if (dbg) d_full += clock64() - w1;
           if (new_b) mbar_wait(&b_full[kb], (bgen - 1) & 1);
           tc_fence_after();
           if (elect_one()) {
             const uint64_t da = descA0 + STAGE_STEP * stage;
             const uint64_t db = descB0 + STAGE_STEP * (bstat ? kb : stage);
-            if (dbgmode != 2) {
+            if ((dbgmode != 2 && dbgmode != 6)) {
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) {
                 if (NCTA == 2) umma_f16_ss_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
@@ -457,7 +460,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
       constexpr int NCH = BN / 32;
       bool first = true;
       int it = 0;
-      const bool dbg = kRoleTimers && dbgmode == 5 && blockIdx.x == 0;
+      const bool dbg = kRoleTimers && dbgtime && blockIdx.x == 0;
       long long d_c = 0, d_r = 0;
       for (int ti = 0, tile = t_begin; ti < t_count; ++ti, tile += t_step, ++it) {
         const int tcol = tile_col(tile);
@@ -522,7 +525,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
     const uint32_t te_addr0 = (NCTA == 2) ? mapa_shared(smem_u32(&tmem_empty[0]), 0) : smem_u32(&tmem_empty[0]);
     int acc = 0, it = 0;
     uint32_t acc_phase = 0;
-    const bool dbg = kRoleTimers && dbgmode == 5 && blockIdx.x == 0 && warp == 2;
+    const bool dbg = kRoleTimers && dbgtime && blockIdx.x == 0 && warp == 2;
     long long d_t0 = dbg ? clock64() : 0, d_tf = 0, d_rf = 0;
     for (int ti = 0, tile = t_begin; ti < t_count; ++ti, tile += t_step, ++it) {
       const int tcol = tile_col(tile);
@@ -603,7 +606,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
             }
           }
           { const long long w0 = dbg ? clock64() : 0; mbar_wait(&r_full[c], (uint32_t)(it & 1)); if (dbg) d_rf += clock64() - w0; }
-          if (dbgmode == 3) {
+          if ((dbgmode == 3 || dbgmode == 6 || dbgmode == 7)) {
           } else if (gemm_stream_bf16(MODE)) {
             // 32 bf16 = 64 B per row; TMA SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3
             uint8_t* rowp = staging + c * S::RCHUNK_BYTES + r * 64;
@@ -748,7 +751,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
             __syncwarp();
             if (lane == 0) release_acc(acc);
           }
-          if (dbgmode == 3) continue;
+          if ((dbgmode == 3 || dbgmode == 6 || dbgmode == 7)) continue;
           const int n0 = n_base + c * 32;
           float f[32];
 #pragma unroll

@@ -13,6 +13,7 @@ M = 172032
 a = torch.randn(M, 320, device="cuda").to(torch.bfloat16)
 a4 = torch.randn(M, 1280, device="cuda").to(torch.bfloat16)
 res = torch.randn(M, 320, device="cuda")
+res16 = res.to(torch.bfloat16)
 def w(n, k): return (torch.randn(n, k, device="cuda") * 0.02).to(torch.bfloat16)
 w_lin, w_qkv, w_ff1, w_ff2 = w(320, 320), w(960, 320), w(2560, 320), w(320, 1280)
 b320 = torch.randn(320, device="cuda"); b2560 = torch.randn(2560, device="cuda")
@@ -21,11 +22,13 @@ rows = [
     ("qkv bf16", lambda: ops.gemm(a, w_qkv, out_dtype=torch.bfloat16), 2.0 * M * 960 * 320),
     ("ff1 geglu", lambda: ops.gemm(a, w_ff1, bias=b2560, geglu=True, out_dtype=torch.bfloat16), 2.0 * M * 2560 * 320),
     ("ff2+res fp32", lambda: ops.gemm(a4, w_ff2, bias=b320, residual=res), 2.0 * M * 320 * 1280),
+    ("to_out+res bf16", lambda: ops.gemm(a, w_lin, bias=b320, residual=res16, out_dtype=torch.bfloat16), 2.0 * M * 320 * 320),
+    ("ff2+res bf16", lambda: ops.gemm(a4, w_ff2, bias=b320, residual=res16, out_dtype=torch.bfloat16), 2.0 * M * 320 * 1280),
 ]
 for name, fn, fl in rows:
     t = timeit(fn)
     print(f"[{tag}] {name:18s} {t*1e6:8.1f} us {fl/t/1e12:7.1f} TF/s")
-    if os.environ.get("PN_GEMM_DEBUG") == "5":
+    if int(os.environ.get("PN_GEMM_DEBUG", "0")) in (5, 8, 9, 10, 11, 12, 14, 15):
         c = (ctypes.c_ulonglong * 16)()
         ops.lib.pn_debug_gemm_counters(c)
         v = [int(x) for x in c]
