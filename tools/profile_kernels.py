@@ -35,6 +35,8 @@ def main():
     xb = torch.randn(M, C, device=dev).to(BF16)
     w3 = (torch.randn(3 * C, C, device=dev) * C ** -0.5).to(BF16)
     kvt = torch.randn(2, 77, 2 * C, device=dev).to(BF16)
+    b3 = torch.randn(3 * C, device=dev)
+    cs3 = w3.float().sum(dim=1).contiguous()
 
     def run_all():
         ops.gemm(x.view(BT, H, W, C), wc, bias=bias, taps=(3, 3))                       # conv3x3 level 0
@@ -53,6 +55,8 @@ def main():
         ops.attention_temporal(qkv.view(2, 8, H * W, 3 * C), 5)                        # temporal attention T=8
         ops.attention_text(xb.view(2, 8 * H * W, C), kvt, 5)                           # text cross-attention (77 keys)
         ops.groupnorm_pixel(res.view(2, 8, H * W, C), g, bz, 1e-5, True)               # pixel-wise temporal GroupNorm
+        y, stats = ops.gemm(x, w, bias=bias, residual=xb, out_dtype=BF16, ln_stats_out=True)   # out-proj that emits the LayerNorm row sums (MODE 7)
+        ops.gemm(y, w3, bias=b3, out_dtype=BF16, ln=(stats, cs3, 1e-5))                # qkv projection that finishes the folded LayerNorm (MODE 8)
 
     for _ in range(2):
         run_all()
