@@ -17,6 +17,8 @@ from __future__ import annotations
 
 import math
 
+import os
+
 import torch
 
 from .ops import geglu_pack
@@ -74,6 +76,8 @@ class Engine:
         self.wc: PackedWeights | None = None
         self.generation = 0
         self.cond = {"guided": None, "kv": {}, "b": None}     # step-invariant state (prepare_hint / prepare_text)
+        self.two_streams = os.environ.get("PN_TWO_STREAMS", "1") != "0"      # ControlNet || UNet encoder (see eps)
+        self._side = None
 
     # ------------------------------------------------------------------------------------------ packing
     def _pack_trunk(self, P: dict, plan: Plan) -> PackedWeights:
@@ -390,17 +394,25 @@ class Engine:
         outs.append(ops.gemm(self._to_operand(h), W[f"zc{i}.w"], bias=W[f"zc{i}.b"]))
         return outs
 
-    def unet(self, x, t, control):
-        """ControlledUNetModel3D.forward (controlmodel.py:160-202), channels-last; returns eps [frames,H,W,out_ch]."""
-        W, ops = self.wu, self.ops
+    def unet_encode(self, x, t):
+        """Input blocks + middle block of ControlledUNetModel3D.forward (controlmodel.py:160-187): everything that does not
+        need the ControlNet residuals. Returns (h, skips, emb vectors)."""
+        W = self.wu
         embv = self._emb_vectors(W, t)
-        control = list(control)
         hs = []
         h = x
         for blk in self.plan_unet.encoder:
             h = self._run_block(W, blk, h, embv)
             hs.append(h)
         h = self._run_block(W, self.plan_unet.middle, h, embv)
+        return h, hs, embv
+
+    def unet_decode(self, enc, control):
+        """`h += control.pop()`, the output blocks on cat([h, hs.pop() + control.pop()]) and the out head
+        (controlmodel.py:188-202)."""
+        W, ops = self.wu, self.ops
+        h, hs, embv = enc
+        control = list(control)
         h = ops.add_(h, control.pop().view(h.shape))
         for blk in self.plan_unet.decoder:
             skip = hs.pop()
@@ -408,6 +420,10 @@ class Engine:
             h = self._run_block(W, blk, h, embv)
         a = ops.groupnorm(h, W["out.g"], W["out.bn"], 1e-5, True, out_f32=ops.act_dtype == F32)
         return ops.conv3x3_direct(a, W["out.w"], W["out.b"], self.cfg.out_channels)
+
+    def unet(self, x, t, control):
+        """ControlledUNetModel3D.forward (controlmodel.py:160-202), channels-last; returns eps [frames,H,W,out_ch]."""
+        return self.unet_decode(self.unet_encode(x, t), control)
 
     def eps(self, x_nchw, concat_nchw, t):
         """OpenAIWrapperControlLDM3D.forward (wrappers.py:37-70) with the step-invariant parts precomputed."""
@@ -419,6 +435,24 @@ class Engine:
         ops.nchw_to_nhwc(x_nchw, out=xin, ch_off=0)
         if concat_nchw is not None:
             ops.nchw_to_nhwc(concat_nchw, out=xin, ch_off=Cx)
-        control = self.controlnet(xin, t)
-        e = self.unet(xin, t, control)
+        if self.two_streams and xin.is_cuda:
+            # The ControlNet and the UNet's own encoder + middle block only meet at the first skip join (controlmodel.py:
+            # 176-195): they run on two streams (a fork / join pair of events, captured into the step's CUDA graph like
+            # everything else). The big level-0/1 kernels are persistent and fill all SMs either way; what overlaps is
+            # the under-filled tail — level-2/3/mid GEMMs and attentions with fewer tiles than SMs, small norms:
+            # 112.4 -> 111.1 ms per step on the same box (PN_TWO_STREAMS=0 for the single-stream order). Giving each branch
+            # a fixed share of the SMs (74/100/120 per branch) instead of letting the kernels queue was measured and is not
+            # better (112.3 / 115.5 / 113.7 ms).
+            cur = torch.cuda.current_stream(xin.device)
+            if self._side is None or self._side.device != xin.device:
+                self._side = torch.cuda.Stream(device=xin.device)
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                control = self.controlnet(xin, t)
+            enc = self.unet_encode(xin, t)
+            cur.wait_stream(self._side)
+            e = self.unet_decode(enc, control)
+        else:
+            control = self.controlnet(xin, t)
+            e = self.unet(xin, t, control)
         return ops.nhwc_to_nchw(e)
