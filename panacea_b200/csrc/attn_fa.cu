@@ -75,6 +75,18 @@ struct FaParams {
   long long out_ld;            // token stride of out (elements)
 };
 
+// Timeline of CTA 0 (diagnostics builds, PN_ATTN_DEBUG=8): clock64 stamps of the two softmax groups and of the UMMA issuer
+// per key block — tools/attn_timeline.py prints the phase durations.
+//  group g (0|1), block n: [g][n][0] S ready  [1] S in registers  [2] row maximum done  [3] past the rendezvous
+//  [4] exponentials done  [5] previous PV retired  [6] P stored;   issuer: [2][n][0|1] S issued (slot A|B), [2|3] PV issued
+#ifdef PN_GEMM_ROLE_TIMERS
+constexpr int FA_TL_BLOCKS = 96;
+__device__ long long g_fa_tl[3][FA_TL_BLOCKS][8];
+#define FA_STAMP(cond, g, n, e) do { if ((cond) && (n) < (uint32_t)FA_TL_BLOCKS) g_fa_tl[g][n][e] = clock64(); } while (0)
+#else
+#define FA_STAMP(cond, g, n, e) do { } while (0)
+#endif
+
 struct FaItem {
   int t0, head, view, frame, nblk;
   bool has_b;
@@ -234,6 +246,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
                 }
               }
               umma_commit(&pv_done[sl]);
+              FA_STAMP(dbgmode == 8 && blockIdx.x == 0, 2, n_pv[sl], 2 + sl);
               if (sl == 1 || !pend_b) umma_commit(&kv_empty[st]);
             }
             ++n_pv[sl];
@@ -264,6 +277,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
                     umma_f16_ss(tmem_base + sl * L::S_STRIDE, dQx0 + XTILE_STEP * (qb * 2 + sl), dKx0 + XTILE_STEP * st, idesc_s, 1u);
                 }
                 umma_commit(&s_full[sl]);
+                FA_STAMP(dbgmode == 8 && blockIdx.x == 0, 2, n_s[sl], sl);
                 // every S MMA reading this Q pair has retired
                 if (j == t.nblk - 1 && (sl == 1 || !t.has_b)) umma_commit(&q_empty[qb]);
               }
@@ -346,13 +360,16 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
       // block per tile (text: 77 keys) the hand-over only adds latency (84 vs 73 us)
       const bool turns = t.has_b && t.nblk > 1 && dbgmode != 4;
       for (int j = 0; j < t.nblk; ++j, ++n) {
+        const bool tl = dbgmode == 8 && blockIdx.x == 0 && lane_grp == 0 && lane == 0;
         mbar_wait(&s_full[sl], n & 1);
+        FA_STAMP(tl, sl, n, 0);
         tc_fence_after();
         uint32_t sv[8][16];
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch)
           if (ch < nchunk) tmem_ld_32x16(tS + ch * 16, sv[ch]);
         tmem_ld_wait();
+        FA_STAMP(tl, sl, n, 1);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_free[sl]);      // the tensor core may overwrite S_t with the next block
@@ -388,7 +405,9 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
         // one block of each other (measured: 550 us with it, 637 us free-running at level 0). Forcing the exponentials
         // behind the barrier (a true alternation of the exp2 phases, r02 experiment) serialises the groups' non-MUFU work
         // with each other's exponentials and is slower (611 us).
+        FA_STAMP(tl, sl, n, 2);
         if (turns) named_bar_sync(1 + sl, 256);
+        FA_STAMP(tl, sl, n, 3);
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) {
           if (ch < nchunk) {
@@ -415,9 +434,11 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
           // depend (vacuously — a row sum is never this NaN pattern) on the sum of all of them
           if (turns) named_bar_arrive(2 - sl, 256u + (__float_as_uint(rs) == 0x7fc0beefu ? 32u : 0u));
           l_run = l_run * alpha + rs;
+          FA_STAMP(tl && rs >= 0.f, sl, n, 4);
         }
         // P_t / O_t may only be touched once the previous PV of this tile slot has retired
         mbar_wait(&pv_done[sl], (n & 1) ^ 1);
+        FA_STAMP(tl, sl, n, 5);
         tc_fence_after();
         if (j == 0) {
           if (have_prev) epilogue(prev_ti, prev_head, prev_view, prev_frame, l_prev);
@@ -454,6 +475,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) attn_fa_kernel(const __grid_con
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[sl]);
+        FA_STAMP(tl, sl, n, 6);
       }
       have_prev = true;
       prev_ti = t.t0 + sl; prev_head = t.head; prev_view = t.view; prev_frame = t.frame;
@@ -591,3 +613,13 @@ extern "C" int pn_attention(const pn_attn_args* a, void* stream_v) {
   PN_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(FA_THREADS), smem_total, reinterpret_cast<cudaStream_t>(stream_v), 1, p));
   return PN_OK;
 }
+
+#ifdef PN_GEMM_ROLE_TIMERS
+// diagnostics (not part of the product ABI): the timeline of CTA 0 of the last pn_attention launch made with PN_ATTN_DEBUG=8
+extern "C" int pn_debug_attn_timeline(long long* out, int n) {
+  PN_CHECK_CUDA(cudaDeviceSynchronize());
+  const size_t bytes = sizeof(long long) * (size_t)(n < 3 * pn::FA_TL_BLOCKS * 8 ? n : 3 * pn::FA_TL_BLOCKS * 8);
+  PN_CHECK_CUDA(cudaMemcpyFromSymbol(out, pn::g_fa_tl, bytes));
+  return PN_OK;
+}
+#endif
