@@ -178,10 +178,10 @@ int pn_cast_operand(const float* x, void* y, int64_t rows, int64_t C, int operan
 /* Parity-mode GEGLU (attention.py:97-99, exact erf GELU) on the fp32 output of the ff.net.0 GEMM whose columns are in
  * pn_gemm's GEGLU packing (blocks of 32 = 16 value + 16 gate columns): in fp32 [rows, 2*inner] -> operand [rows, inner]. */
 int pn_geglu_operand(const float* in, void* y, int64_t rows, int64_t inner, int operand_mode, void* stream);
-/* [batch, A, B] -> out[batch, B, ld] at column offset off: NCHW <-> channels-last at the module boundary
- * (also performs the channel concat of wrappers.py:41). */
-int pn_transpose_f32(const float* in, float* out, int64_t batch, int64_t A, int64_t B, int64_t out_ld, int64_t out_off,
-                     void* stream);
+/* in[batch, A, first B of in_ld columns] -> out[batch, B, ld] at column offset off: NCHW <-> channels-last at the module
+ * boundary (also performs the channel concat of wrappers.py:41, and drops the padding columns of the out-head GEMM). */
+int pn_transpose_f32(const float* in, float* out, int64_t batch, int64_t A, int64_t B, int64_t in_ld, int64_t out_ld,
+                     int64_t out_off, void* stream);
 /* util.py:224-248 timestep_embedding (cos | sin halves). freqs: optional fp32 [dim/2] frequency table computed by the
  * host with the reference's expression (bit-identical arguments t*f); NULL = computed in the kernel. */
 int pn_timestep_embedding(const int64_t* t, float* out, int64_t n, int64_t dim, const float* freqs, void* stream);

@@ -9,17 +9,17 @@
 namespace pn {
 
 // ---------------------------------------------------------------- [F, A, B] -> out[f, b, off + a] (row stride ld)
-__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int A, int B, long long ld,
-                                 int off) {
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int A, int B, long long in_ld,
+                                 long long ld, int off) {
   pdl_prologue_done();
   __shared__ float tile[32][33];
   const int f = blockIdx.z;
   const int b0 = blockIdx.x * 32, a0 = blockIdx.y * 32;
-  const float* src = in + (size_t)f * A * B;
+  const float* src = in + (size_t)f * A * in_ld;
   float* dst = out + (size_t)f * B * ld;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int a = a0 + i, b = b0 + threadIdx.x;
-    if (a < A && b < B) tile[i][threadIdx.x] = src[(size_t)a * B + b];
+    if (a < A && b < B) tile[i][threadIdx.x] = src[(size_t)a * in_ld + b];
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -340,13 +340,13 @@ static inline int grid_for(size_t total, int threads = 256) {
 
 using namespace pn;
 
-extern "C" int pn_transpose_f32(const float* in, float* out, int64_t batch, int64_t A, int64_t B, int64_t out_ld,
+extern "C" int pn_transpose_f32(const float* in, float* out, int64_t batch, int64_t A, int64_t B, int64_t in_ld, int64_t out_ld,
                                 int64_t out_off, void* stream_v) {
-  PN_REQUIRE(in && out && batch > 0 && A > 0 && B > 0 && out_ld >= out_off + A, "pn_transpose_f32: bad arguments");
+  PN_REQUIRE(in && out && batch > 0 && A > 0 && B > 0 && in_ld >= B && out_ld >= out_off + A, "pn_transpose_f32: bad arguments");
   PN_REQUIRE(batch <= 65535, "pn_transpose_f32: batch too large");
   dim3 grid((unsigned)((B + 31) / 32), (unsigned)((A + 31) / 32), (unsigned)batch);
-  launch_kernel(transpose_kernel, dim3(grid), dim3(dim3(32, 8)), 0, reinterpret_cast<cudaStream_t>(stream_v), 1, in, out, (int)A, (int)B, out_ld,
-                                                                                         (int)out_off);
+  launch_kernel(transpose_kernel, dim3(grid), dim3(dim3(32, 8)), 0, reinterpret_cast<cudaStream_t>(stream_v), 1, in, out, (int)A, (int)B, (long long)in_ld,
+                                                                                         (long long)out_ld, (int)out_off);
   PN_CHECK_CUDA(cudaGetLastError());
   return PN_OK;
 }

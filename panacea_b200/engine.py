@@ -44,6 +44,10 @@ class PackedWeights(dict):
     tag = ""
 
 
+STEM_CPAD = 64       # input channels of the stem conv padded to one 64-channel swizzle atom
+OUT_NPAD = 8         # output channels of the out-head conv padded to the GEMM's minimum N
+
+
 def _conv3_matrix(w):      # [Cout, Cin, 3, 3] -> fp32 [Cout, (ky, kx, ci)]
     return w.detach().to(F32).permute(0, 2, 3, 1).reshape(w.shape[0], -1)
 
@@ -76,6 +80,7 @@ class Engine:
         self.wc: PackedWeights | None = None
         self.generation = 0
         self.cond = {"guided": None, "kv": {}, "b": None}     # step-invariant state (prepare_hint / prepare_text)
+        self._xin, self._xin_key = None, None
         self.two_streams = os.environ.get("PN_TWO_STREAMS", "1") != "0"      # ControlNet || UNet encoder (see eps)
         self._side = None
 
@@ -90,7 +95,11 @@ class Engine:
         for st in plan.stages():
             k = st.key
             if st.kind == "stem":
-                W[k + ".w"] = _pack_direct(P[k + ".weight"].detach()); W[k + ".b"] = f(P[k + ".bias"])
+                # the 8 -> 320 input conv runs on the tensor-core conv kernel with its input channels zero-padded to one
+                # 64-channel atom (the CUDA-core direct conv took 660 us per network at level 0; this is ~70 us)
+                w_in = P[k + ".weight"].detach().to(F32)
+                w_in = torch.nn.functional.pad(w_in, (0, 0, 0, 0, 0, STEM_CPAD - w_in.shape[1]))
+                W[k + ".w"] = mat(_conv3_matrix(w_in), 9); W[k + ".b"] = f(P[k + ".bias"])
             elif st.kind == "res":
                 for nm in ("in_layers.0", "in_layers_temporal.0", "out_layers.0", "out_layers_temporal.0"):
                     W[f"{k}.{nm}.g"] = f(P[f"{k}.{nm}.weight"]); W[f"{k}.{nm}.b"] = f(P[f"{k}.{nm}.bias"])
@@ -173,7 +182,11 @@ class Engine:
             wu = self._pack_trunk(unet_params, self.plan_unet)
             wu.tag = "unet"
             wu["out.g"] = f(unet_params["out.0.weight"]); wu["out.bn"] = f(unet_params["out.0.bias"])
-            wu["out.w"] = _pack_direct(unet_params["out.2.weight"].detach()); wu["out.b"] = f(unet_params["out.2.bias"])
+            # the 320 -> 4 output conv as a GEMM whose N is zero-padded to 8 (the narrowest the epilogue stores)
+            w_out = unet_params["out.2.weight"].detach().to(F32)
+            n_pad = OUT_NPAD - w_out.shape[0]
+            wu["out.w"] = self.ops.pack_matrix(_conv3_matrix(torch.nn.functional.pad(w_out, (0, 0, 0, 0, 0, 0, 0, n_pad))), 9)
+            wu["out.b"] = torch.nn.functional.pad(f(unet_params["out.2.bias"]), (0, n_pad)).contiguous()
             self.wu = wu
         if cn_params is not None:
             wc = self._pack_trunk(cn_params, self.plan_cn)
@@ -250,8 +263,11 @@ class Engine:
         ops = self.ops
         te = ops.timestep_embedding(t, self.cfg.model_channels)
         e = ops.linear_small(te, W["te0.w"], W["te0.b"], silu_out=True)
-        e = ops.linear_small(e, W["te2.w"], W["te2.b"])
-        return ops.linear_small(e, W["emb.w"], W["emb.b"], silu_in=True)
+        # every consumer of `emb` is Sequential(SiLU, Linear) (openaimodel.py:439-445): the SiLU is applied ONCE, in the
+        # epilogue of time_embed's second Linear — as `silu_in` of the big [sum(Cout), 1280] projection each of its 5,000
+        # warps recomputed it for all 16 x 1280 inputs (2 MUFU each): 1.0 ms per step for two GEMVs
+        e = ops.linear_small(e, W["te2.w"], W["te2.b"], silu_out=True)
+        return ops.linear_small(e, W["emb.w"], W["emb.b"])
 
     def _res(self, W, st: Stage, x, embv):
         """ResBlock3D._forward (openaimodel.py:499-542)."""
@@ -364,7 +380,7 @@ class Engine:
         ops = self.ops
         for st in blk:
             if st.kind == "stem":
-                h = ops.conv3x3_direct(h, W[st.key + ".w"], W[st.key + ".b"], st.cout, addend=guided)
+                h = ops.gemm(h, W[st.key + ".w"], bias=W[st.key + ".b"], taps=(3, 3), residual=guided)      # h: stem operand
             elif st.kind == "res":
                 h = self._res(W, st, h, embv)
             elif st.kind == "stt":
@@ -385,7 +401,7 @@ class Engine:
         W, ops = self.wc, self.ops
         embv = self._emb_vectors(W, t)
         outs = []
-        h = x
+        h = self.stem_operand(x)
         for i, blk in enumerate(self.plan_cn.encoder):
             h = self._run_block(W, blk, h, embv, guided=self.cond["guided"] if i == 0 else None)
             outs.append(ops.gemm(self._to_operand(h), W[f"zc{i}.w"], bias=W[f"zc{i}.b"]))
@@ -400,7 +416,7 @@ class Engine:
         W = self.wu
         embv = self._emb_vectors(W, t)
         hs = []
-        h = x
+        h = self.stem_operand(x)
         for blk in self.plan_unet.encoder:
             h = self._run_block(W, blk, h, embv)
             hs.append(h)
@@ -418,23 +434,39 @@ class Engine:
             skip = hs.pop()
             h = ops.concat_add(h, skip, control.pop().view(skip.shape))
             h = self._run_block(W, blk, h, embv)
-        a = ops.groupnorm(h, W["out.g"], W["out.bn"], 1e-5, True, out_f32=ops.act_dtype == F32)
-        return ops.conv3x3_direct(a, W["out.w"], W["out.b"], self.cfg.out_channels)
+        a = ops.groupnorm(h, W["out.g"], W["out.bn"], 1e-5, True)
+        return ops.gemm(a, W["out.w"], bias=W["out.b"], taps=(3, 3))      # [frames,H,W,OUT_NPAD]: channels >= out_channels are 0
 
     def unet(self, x, t, control):
-        """ControlledUNetModel3D.forward (controlmodel.py:160-202), channels-last; returns eps [frames,H,W,out_ch]."""
+        """ControlledUNetModel3D.forward (controlmodel.py:160-202), channels-last x [frames,H,W,in_channels] (or the stem
+        operand); returns eps [frames,H,W,OUT_NPAD] whose first out_channels channels are the prediction."""
         return self.unet_decode(self.unet_encode(x, t), control)
+
+    def stem_operand(self, x):
+        """fp32 channels-last network input [frames,H,W,in_channels] -> the MMA operand of the input conv: channels
+        zero-padded to STEM_CPAD. A tensor that already has STEM_CPAD channels (the buffer eps() fills) is only cast."""
+        if x.dtype != F32:
+            return x                                     # already an operand
+        if x.shape[-1] != STEM_CPAD:
+            xp = torch.zeros((*x.shape[:-1], STEM_CPAD), device=x.device, dtype=F32)      # module-level entry points only
+            xp[..., :x.shape[-1]] = x
+            x = xp
+        return self.ops.cast_operand(x)
 
     def eps(self, x_nchw, concat_nchw, t):
         """OpenAIWrapperControlLDM3D.forward (wrappers.py:37-70) with the step-invariant parts precomputed."""
         ops = self.ops
         assert self.cond is not None and self.cond["guided"] is not None and self.cond["kv"], "call prepare_condition() first"
         Fr, Cx, H, Wd = x_nchw.shape
-        cin = self.cfg.in_channels
-        xin = torch.empty((Fr, H, Wd, cin), device=x_nchw.device, dtype=F32)
+        key = (Fr, H, Wd, str(x_nchw.device))
+        if self._xin is None or self._xin_key != key:
+            # channels in_channels..STEM_CPAD-1 stay zero for the life of the buffer (stable address: graph-friendly)
+            self._xin, self._xin_key = torch.zeros((Fr, H, Wd, STEM_CPAD), device=x_nchw.device, dtype=F32), key
+        xin = self._xin
         ops.nchw_to_nhwc(x_nchw, out=xin, ch_off=0)
         if concat_nchw is not None:
             ops.nchw_to_nhwc(concat_nchw, out=xin, ch_off=Cx)
+        xin = ops.cast_operand(xin)                     # one operand for both input convs (ControlNet and UNet)
         if self.two_streams and xin.is_cuda:
             # The ControlNet and the UNet's own encoder + middle block only meet at the first skip join (controlmodel.py:
             # 176-195): they run on two streams (a fork / join pair of events, captured into the step's CUDA graph like
@@ -455,4 +487,4 @@ class Engine:
         else:
             control = self.controlnet(xin, t)
             e = self.unet(xin, t, control)
-        return ops.nhwc_to_nchw(e)
+        return ops.nhwc_to_nchw(e, channels=self.cfg.out_channels)

@@ -346,15 +346,18 @@ class NativeOps:
         Fr, Cc, H, W = x.shape
         if out is None:
             out = torch.empty((Fr, H, W, Cc), device=x.device, dtype=F32)
-        _lib.check(self.lib.pn_transpose_f32(_ptr(x), _ptr(out), Fr, Cc, H * W, out.shape[-1], ch_off, _stream()), "pn_transpose_f32")
+        _lib.check(self.lib.pn_transpose_f32(_ptr(x), _ptr(out), Fr, Cc, H * W, H * W, out.shape[-1], ch_off, _stream()), "pn_transpose_f32")
         self.launches += 1
         return out
 
-    def nhwc_to_nchw(self, x):
+    def nhwc_to_nchw(self, x, channels=None):
+        """x fp32 [F,H,W,C] -> [F, channels or C, H, W] (the first `channels` of C: the out-head GEMM pads its N to 8)."""
         _req(x.is_cuda and x.dtype == F32 and x.is_contiguous() and x.dim() == 4, "nhwc_to_nchw: x fp32 [F,H,W,C]")
-        Fr, H, W, Cc = x.shape
+        Fr, H, W, ld = x.shape
+        Cc = ld if channels is None else channels
+        _req(0 < Cc <= ld, "nhwc_to_nchw: channels out of range")
         out = torch.empty((Fr, Cc, H, W), device=x.device, dtype=F32)
-        _lib.check(self.lib.pn_transpose_f32(_ptr(x), _ptr(out), Fr, H * W, Cc, H * W, 0, _stream()), "pn_transpose_f32")
+        _lib.check(self.lib.pn_transpose_f32(_ptr(x), _ptr(out), Fr, H * W, Cc, ld, H * W, 0, _stream()), "pn_transpose_f32")
         self.launches += 1
         return out
 

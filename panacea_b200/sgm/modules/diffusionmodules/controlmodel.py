@@ -238,4 +238,4 @@ class ControlledUNetModel3D(_FlatParams):
         ctrl = [ops.nchw_to_nhwc(c.float().contiguous()) for c in control]
         del control[:]                                            # the reference pops every entry (controlmodel.py:192-195)
         e = eng.unet(ops.nchw_to_nhwc(x.float().contiguous()), timesteps.to(torch.int64).contiguous(), ctrl)
-        return ops.nhwc_to_nchw(e)
+        return ops.nhwc_to_nchw(e, channels=self.cfg.out_channels)

@@ -187,8 +187,8 @@ class TorchRefOps:
         out[..., ch_off:ch_off + x.shape[1]] = y
         return out
 
-    def nhwc_to_nchw(self, x):
-        return x.permute(0, 3, 1, 2).contiguous()
+    def nhwc_to_nchw(self, x, channels=None):
+        return (x if channels is None else x[..., :channels]).permute(0, 3, 1, 2).contiguous()
 
     def timestep_embedding(self, t, dim):
         half = dim // 2
