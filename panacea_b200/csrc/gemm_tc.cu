@@ -680,6 +680,7 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
                                                  // a third chunk spills, and a spilled prefetch stalls on its own load)
     int acc = 0;
     uint32_t acc_phase = 0;
+    int bias_col = -1;                           // column tile whose bias slice sits in my_bias
     // hand-back target: the leader CTA's tmem_empty barrier (remote arrive from the peer CTA of a pair)
     const uint32_t te_addr0 = (NCTA == 2) ? mapa_shared(smem_u32(&tmem_empty[0]), 0) : smem_u32(&tmem_empty[0]);
     auto release_acc = [&](int a) {
@@ -705,12 +706,13 @@ __global__ void __launch_bounds__(gemm_threads(MODE), 1) gemm_tc_kernel(const __
       const int n_base = tcol * BN;
       // bias slice of this warp's chunks -> shared memory now, while the accumulator is still being computed (a global
       // load per chunk inside the epilogue left the warps on the long scoreboard for a third of their time)
-      if (S::BIAS_SMEM && p.bias != nullptr) {
+      if (S::BIAS_SMEM && p.bias != nullptr && tcol != bias_col) {     // (the weight-stationary schedule keeps one column tile)
 #pragma unroll
         for (int k = 0; k < MYCH; ++k) {
           const int n = n_base + (half + EG * k) * 32 + lane;
           my_bias[k * 32 + lane] = (half + EG * k < NCH && n < p.N) ? __ldg(p.bias + n) : 0.f;
         }
+        bias_col = tcol;
       }
       __syncwarp();
       const int my_row = my_rowmap[lane];
