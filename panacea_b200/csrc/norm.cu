@@ -382,7 +382,8 @@ using namespace pn;
 // wave = frames processed concurrently (their input fits L2), cpf = CTAs per frame; wave * cpf <= SM count
 static void gn_geometry(int64_t frames, int64_t pixels, int64_t channels, int* wave, int* cpf) {
   const size_t frame_bytes = (size_t)pixels * channels * sizeof(float);
-  int w = (int)(GN_WAVE_BYTES / (frame_bytes ? frame_bytes : 1));
+  static const size_t wave_bytes = [] { const char* e = std::getenv("PN_GN_WAVE_MB"); return e ? (size_t)std::atoi(e) << 20 : GN_WAVE_BYTES; }();
+  int w = (int)(wave_bytes / (frame_bytes ? frame_bytes : 1));
   if (w < 1) w = 1;
   if (w > frames) w = (int)frames;
   const int sms = sm_count();
