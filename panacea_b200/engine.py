@@ -80,7 +80,7 @@ class Engine:
         self.wc: PackedWeights | None = None
         self.generation = 0
         self.cond = {"guided": None, "kv": {}, "b": None}     # step-invariant state (prepare_hint / prepare_text)
-        self._xin, self._xin_key = None, None
+        self._xin = {}
         self.two_streams = os.environ.get("PN_TWO_STREAMS", "1") != "0"      # ControlNet || UNet encoder (see eps)
         self._side = None
 
@@ -459,10 +459,11 @@ class Engine:
         assert self.cond is not None and self.cond["guided"] is not None and self.cond["kv"], "call prepare_condition() first"
         Fr, Cx, H, Wd = x_nchw.shape
         key = (Fr, H, Wd, str(x_nchw.device))
-        if self._xin is None or self._xin_key != key:
-            # channels in_channels..STEM_CPAD-1 stay zero for the life of the buffer (stable address: graph-friendly)
-            self._xin, self._xin_key = torch.zeros((Fr, H, Wd, STEM_CPAD), device=x_nchw.device, dtype=F32), key
-        xin = self._xin
+        if key not in self._xin:
+            # channels in_channels..STEM_CPAD-1 stay zero for the life of the buffer. One buffer per input geometry, never
+            # freed: a CUDA graph captured for an earlier geometry keeps replaying into ITS buffer
+            self._xin[key] = torch.zeros((Fr, H, Wd, STEM_CPAD), device=x_nchw.device, dtype=F32)
+        xin = self._xin[key]
         ops.nchw_to_nhwc(x_nchw, out=xin, ch_off=0)
         if concat_nchw is not None:
             ops.nchw_to_nhwc(concat_nchw, out=xin, ch_off=Cx)
