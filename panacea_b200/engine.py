@@ -98,6 +98,8 @@ class Engine:
                 # the 8 -> 320 input conv runs on the tensor-core conv kernel with its input channels zero-padded to one
                 # 64-channel atom (the CUDA-core direct conv took 660 us per network at level 0; this is ~70 us)
                 w_in = P[k + ".weight"].detach().to(F32)
+                if w_in.shape[1] > STEM_CPAD:
+                    raise NotImplementedError(f"input conv with {w_in.shape[1]} > {STEM_CPAD} channels")
                 w_in = torch.nn.functional.pad(w_in, (0, 0, 0, 0, 0, STEM_CPAD - w_in.shape[1]))
                 W[k + ".w"] = mat(_conv3_matrix(w_in), 9); W[k + ".b"] = f(P[k + ".bias"])
             elif st.kind == "res":
@@ -184,6 +186,8 @@ class Engine:
             wu["out.g"] = f(unet_params["out.0.weight"]); wu["out.bn"] = f(unet_params["out.0.bias"])
             # the 320 -> 4 output conv as a GEMM whose N is zero-padded to 8 (the narrowest the epilogue stores)
             w_out = unet_params["out.2.weight"].detach().to(F32)
+            if w_out.shape[0] > OUT_NPAD:
+                raise NotImplementedError(f"output conv with {w_out.shape[0]} > {OUT_NPAD} channels")
             n_pad = OUT_NPAD - w_out.shape[0]
             wu["out.w"] = self.ops.pack_matrix(_conv3_matrix(torch.nn.functional.pad(w_out, (0, 0, 0, 0, 0, 0, 0, n_pad))), 9)
             wu["out.b"] = torch.nn.functional.pad(f(unet_params["out.2.bias"]), (0, n_pad)).contiguous()
