@@ -1070,8 +1070,12 @@ extern "C" int pn_gemm(const pn_gemm_args* a, void* stream_v) {
   const long long tiles_m_1 = (long long)p.tiles_w * p.tiles_h * p.tiles_n;
   int BN, NCTA = 1;
   const int force = gemm_mode_override();     // PN_GEMM_MODE=1|2 (debug / A-B measurements)
-  if (a->N % 256 == 0 && (force == 2 || (force == 0 && tiles_m_1 * (a->N / 256) >= 2 * sm_count()))) { BN = 256; NCTA = 2; }
-  else if (a->N % 160 == 0 && (force == 2 || (force == 0 && tiles_m_1 * (a->N / 160) >= 2 * sm_count()))) { BN = 160; NCTA = 2; }
+  // (a single-CTA 128 x N tile is L2->SM bound — 10.9 TB/s of operand traffic at 0.8 PF on the level-3 convs —, so pairs win
+  // as soon as they keep half of the SMs busy: 99 -> 68 us and 188 -> 118 us for the 1280- and 2560-channel 3x3 convs on
+  // 2,688 rows, tools/smallm_probe.py; they used to need two full waves of tiles)
+  const long long pair_min = sm_count() / 2;
+  if (a->N % 256 == 0 && (force == 2 || (force == 0 && tiles_m_1 * (a->N / 256) >= pair_min))) { BN = 256; NCTA = 2; }
+  else if (a->N % 160 == 0 && (force == 2 || (force == 0 && tiles_m_1 * (a->N / 160) >= pair_min))) { BN = 160; NCTA = 2; }
   else if (a->N % 160 == 0) BN = 160;
   else if (a->N >= 128) BN = 128;
   else if (a->N > 32) BN = 64;
